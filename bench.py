@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the DeepFwFM forward hot path (BASELINE.json metric: inference samples/s + roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|fp32_csr]
+
+A step = one forward of one synthetic Criteo-shaped batch (BASELINE config 2: DeepFwFM dense, fwfm+deep+fwlw,
+MLP 400x400x400, paper-Criteo cardinalities, B = 4096 per GPU).  Prints ONE JSON line (rank 0).
+
+  value     samples/s with inputs resident in HBM: K steps replayed from CUDA graphs over distinct batches,
+            CUDA events on the launch stream, max over ranks
+  e2e       samples/s through the host-buffer C-ABI call dfw_forward_host: pinned host batches -> H2D -> kernels
+            -> sigmoid -> D2H -> sync, every step inside the timed region
+  roofline  the dominant kernel stage, timed live with CUDA events (algorithmic bytes / flops per SURVEY 8(d))
+  cpu_baseline / --impl reference: oracle/torch_port.py (the reference's op sequence, fp32 torch CPU) on the
+            host cores -- the reference is a Python module and does not travel to the GPU box; kind "port"
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "DeepFwFM inference samples/sec"
+UNIT = "samples/s"
+FIELD, NUM, K_EMB, NODES, DEPTH = 39, 13, 10, 400, 3
+ALG_BYTES_PER_SAMPLE = 26 * 8 + 13 * 4 + 26 * K_EMB * 4 + 4          # 1304
+ALG_BYTES_PER_BATCH = 477600 * 4 + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4   # weights read once per launch
+MLP_FLOPS_PER_SAMPLE = 2 * (390 * 400 + 2 * 400 * 400 + 400)          # 952,800
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--precision", default=os.environ.get("DFW_BENCH_PRECISION", "fp32"))
+    ap.add_argument("--nbatches", type=int, default=256, help="distinct input batches cycled (> L2 in total)")
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------- workload
+def make_model(device, precision, feature_sizes):
+    from xsdeepfwfm_deprecated_b200.model import DeepFMs
+    m = DeepFMs(FIELD, feature_sizes, embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False,
+                use_fwfm=True, use_deep=True, use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM,
+                random_seed=42, precision=precision)
+    m = m.to(device)
+    m.init_weights()                       # the reference's init distributions, on the device
+    with torch.no_grad():
+        for f in range(FIELD):
+            m.fm_2nd_embeddings[f].weight.mul_(10.0)      # trained-scale embeddings
+    return m.eval().freeze()
+
+
+def make_batches(device, feature_sizes, B, nb, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cats = torch.tensor(feature_sizes[NUM:], device=device, dtype=torch.float64)
+    u = torch.rand(nb, B, FIELD - NUM, generator=g, device=device, dtype=torch.float64)
+    Xi = (u * cats).long().clamp_(max=int(max(feature_sizes)) - 1)
+    Xi = torch.minimum(Xi, (cats - 1).long()).unsqueeze(-1).contiguous()        # (nb, B, 26, 1) uniform indices
+    Xv = torch.randint(0, 50, (nb, B, NUM), generator=g, device=device).float()
+    return Xi, Xv
+
+
+def time_events(fn, iters, stream):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for i in range(iters):
+        fn(i)
+    b.record(stream)
+    b.synchronize()
+    return a.elapsed_time(b) / iters      # ms per call
+
+
+def run_ours(args):
+    from oracle import synth
+    from xsdeepfwfm_deprecated_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    sizes = synth.CRITEO_PAPER
+    B, nb = args.batch, args.nbatches
+    model = make_model(device, args.precision, sizes)
+    Xi, Xv = make_batches(device, sizes, B, nb, seed=rank)
+    plan = model._get_plan()
+    plan.ensure_image(model, args.precision)
+    prec = _lib.PRECISIONS[args.precision]
+    ws = plan.get_workspace(lib.dfw_forward_workspace_bytes(plan.model_ref, B, prec))
+    logits = torch.empty(nb, B, device=device)
+    stream = torch.cuda.Stream(device)
+    sp = stream.cuda_stream
+
+    def step(i):
+        j = i % nb
+        rc = lib.dfw_forward(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B, prec,
+                             ws.data_ptr(), ws.numel(), logits[j].data_ptr(), None, None, sp)
+        if rc:
+            _lib.check(rc, "dfw_forward")
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    with torch.cuda.stream(stream):
+        for i in range(max(args.warmup, 3)):
+            step(i)
+    barrier()
+    l0 = lib.dfw_launch_count()
+    step(0)
+    launches_per_step = lib.dfw_launch_count() - l0
+    torch.cuda.synchronize(device)
+
+    # K steps as CUDA-graph replays of G-step segments (each segment walks distinct batches)
+    graphs, G = [], 0
+    if args.graph:
+        G = min(16, args.steps)
+        nseg = max(1, min(nb // G, 16))
+        for s in range(nseg):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(G):
+                    step(s * G + i)
+            graphs.append(g)
+
+    def run_steps(k):
+        if not graphs:
+            with torch.cuda.stream(stream):
+                for i in range(k):
+                    step(i)
+            return
+        done, s = 0, 0
+        with torch.cuda.stream(stream):
+            while done + G <= k:
+                graphs[s % len(graphs)].replay()
+                done += G
+                s += 1
+            for i in range(k - done):
+                step(i)
+
+    run_steps(max(args.warmup, 3))
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    run_steps(args.steps)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- per-stage timing for the roofline (live, CUDA events, same stream, same inputs) -------------
+    FK = FIELD * K_EMB
+    ldE, ldEb = (FK + 3) // 4 * 4, (FK + 7) // 8 * 8
+    Bp = (B + 127) // 128 * 128
+    E = torch.zeros(Bp, ldE, device=device)
+    Eb = torch.zeros(Bp, ldEb, device=device, dtype=torch.bfloat16)
+    shallow = torch.zeros(Bp, device=device)
+    mws = torch.zeros(lib.dfw_mlp_workspace_bytes(plan.model_ref, B, prec) + 4096, dtype=torch.uint8, device=device)
+    bf = args.precision == "bf16"
+
+    def embed(i):
+        j = i % nb
+        rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B,
+                                None if bf else E.data_ptr(), ldE, Eb.data_ptr() if bf else None, ldEb,
+                                shallow.data_ptr(), None, 0, sp)
+        if rc:
+            _lib.check(rc, "dfw_embed_fwfm")
+
+    mlp_fn = {"fp32": lib.dfw_mlp_fp32, "fp32_csr": lib.dfw_mlp_csr, "bf16": lib.dfw_mlp_bf16}[args.precision]
+
+    def mlp(i):
+        rc = mlp_fn(plan.model_ref, Eb.data_ptr() if bf else E.data_ptr(), ldEb if bf else ldE, B, shallow.data_ptr(),
+                    mws.data_ptr(), mws.numel(), logits[i % nb].data_ptr(), None, sp)
+        if rc:
+            _lib.check(rc, "dfw_mlp")
+
+    with torch.cuda.stream(stream):
+        for i in range(5):
+            embed(i); mlp(i)
+        torch.cuda.synchronize(device)
+        n_it = max(20, min(args.steps, 200))
+        t_embed = time_events(embed, n_it, stream)
+        t_mlp = time_events(mlp, n_it, stream)
+    pk = peaks()
+    embed_bytes = ALG_BYTES_PER_SAMPLE * B + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4
+    stage = {
+        "embed_fwfm": dict(ms=t_embed, bound="hbm", achieved=embed_bytes / (t_embed * 1e-3) / 1e9, peak=pk["hbm"],
+                           unit="GB/s"),
+        "mlp": dict(ms=t_mlp, bound="tensor", achieved=MLP_FLOPS_PER_SAMPLE * B / (t_mlp * 1e-3) / 1e12,
+                    peak=pk["tf_burst"], unit="TFLOP/s"),
+    }
+    dom = "mlp" if t_mlp >= t_embed else "embed_fwfm"
+    d = stage[dom]
+    roofline = dict(kernel=dom, bound=d["bound"], achieved=round(d["achieved"], 3), peak=d["peak"], unit=d["unit"],
+                    frac=round(d["achieved"] / d["peak"], 5), traffic=None, peak_source=pk["src"],
+                    ms_per_launch=round(d["ms"], 5),
+                    stages={k: dict(ms=round(v["ms"], 5), achieved=round(v["achieved"], 3), unit=v["unit"],
+                                    frac=round(v["achieved"] / v["peak"], 5)) for k, v in stage.items()},
+                    whole_step_hbm_frac=round((ALG_BYTES_PER_SAMPLE * B + ALG_BYTES_PER_BATCH) / (ms_per_step * 1e-3)
+                                              / 1e9 / pk["hbm"], 5))
+
+    # ---- e2e: host buffers through dfw_forward_host ------------------------------------------------------
+    nh = 16
+    hXi = torch.empty(nh, B, 26, dtype=torch.int64).pin_memory()
+    hXv = torch.empty(nh, B, NUM, dtype=torch.float32).pin_memory()
+    hXi.copy_(Xi[:nh, :, :, 0].cpu()); hXv.copy_(Xv[:nh].cpu())
+    hout = torch.empty(nh, B, dtype=torch.float32).pin_memory()
+    hws = torch.zeros(lib.dfw_forward_host_workspace_bytes(plan.model_ref, B, prec) + 4096, dtype=torch.uint8,
+                      device=device)
+
+    def e2e_step(i):
+        j = i % nh
+        rc = lib.dfw_forward_host(plan.model_ref, hXi[j].data_ptr(), hXv[j].data_ptr(), B, prec, hws.data_ptr(),
+                                  hws.numel(), None, hout[j].data_ptr(), sp)
+        if rc:
+            _lib.check(rc, "dfw_forward_host")
+
+    for i in range(max(3, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize(device)
+    t_e2e = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([t_e2e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = dict(value=round(world * B * args.steps / t_e2e, 1), unit=UNIT,
+               h2d_bytes_per_step=B * (26 * 8 + NUM * 4), d2h_bytes_per_step=B * 4,
+               ms_per_step=round(t_e2e / args.steps * 1e3, 4),
+               api="dfw_forward_host (pinned host Xi/Xv -> probabilities in pinned host memory)")
+    clk = clocks.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_baseline(B, args.cpu_seconds)
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "fp32_csr": "f32", "bf16": "bf16 operands, f32 accumulate (shallow part f32)"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: DeepFwFM dense (fwfm+deep+fwlw), F=39 (13 numeric), K=10, MLP "
+                                   "400x400x400, paper-Criteo cardinalities (1.33 M rows, 53 MB fp32), uniform indices",
+                       "batch_per_gpu": B, "precision": args.precision,
+                       "l2": f"inputs cycle over {nb} distinct batches ({nb * B * 260 / 1e6:.0f} MB > 126 MB L2); "
+                             "the 53 MB of tables + 1.9 MB of weights stay L2-resident by design",
+                       "launch": f"CUDA graphs of {G} steps" if graphs else "stream launches",
+                       "tables": "replicated" if world == 1 else "replicated per rank"},
+            "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_setup(B):
+    from oracle import synth, torch_port
+    from oracle.config import PathConfig
+    cfg = PathConfig(FIELD, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    Xi, Xv = synth.make_inputs(cfg, B, seed=0)
+    return cfg, sd, torch.from_numpy(Xi), torch.from_numpy(Xv), torch_port
+
+
+def cpu_port_baseline(B, budget_s):
+    cfg, sd, Xi, Xv, torch_port = cpu_port_setup(B)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch_port.forward(cfg, sd, Xi, Xv)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 50):
+        t0 = time.perf_counter()
+        torch_port.forward(cfg, sd, Xi, Xv)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return dict(value=round(B / statistics.median(times), 1), unit=UNIT, cores=cores, kind="port",
+                best=round(B / best, 1),
+                sample=f"{len(times)} forwards of the same B={B} config-2 batch through oracle/torch_port.py "
+                       f"(reference op sequence, fp32, torch {torch.__version__} CPU, {cores} threads), median")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.batch
+    cfg, sd, Xi, Xv, torch_port = cpu_port_setup(B)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps = min(args.steps, 60)          # bounded: each step is one full B=4096 forward on the CPU (~0.1-0.4 s)
+    for _ in range(min(max(args.warmup, 1), 3)):
+        torch_port.forward(cfg, sd, Xi, Xv)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.forward(cfg, sd, Xi, Xv)
+    dt = time.perf_counter() - t0
+    v = round(B * steps / dt, 1)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": min(max(args.warmup, 1), 3), "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE config 2 (same as the GPU arm), one B=4096 batch per step on the host CPU",
+                      "batch_per_gpu": B},
+           "cpu_baseline": dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                sample=f"{steps} forwards of B={B} through oracle/torch_port.py (the reference's op "
+                                       f"sequence, fp32 torch CPU, {cores} threads); the reference itself is a Python "
+                                       "module under /root/reference and does not travel to the GPU box"),
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,209 @@
+/*
+ * deepfwfm_b200.h -- C ABI of libdeepfwfm_sm100a.so
+ *
+ * B200-native (sm_100a) implementation of the DeepFwFM / DeepLight forward hot path:
+ * the body of `DeepFMs.forward(Xi, Xv)` of ShanningLiu/xsDeepFwFM_deprecated
+ * (reference: model/DeepFMs.py:285-469 and model/QREmbeddingBag.py:156-174).
+ *
+ * The reference has no native interface for this path -- it is a chain of ~130 eager aten
+ * calls inside one Python method.  The entry points below are what a binding for that
+ * method binds instead; each one cites the reference lines it replaces.  The Python host
+ * (xsdeepfwfm_deprecated_b200/model/DeepFMs.py) loads this library with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a raw device pointer unless named *_host
+ *   - sizes are int64_t / int32_t, `stream` is a cudaStream_t passed as void*
+ *   - every function returns int: 0 ok, <0 argument/ABI error (DFW_E_*), >0 a cudaError_t;
+ *     nothing throws across the boundary; dfw_last_error_string() describes the last failure
+ *     of the calling thread
+ *   - all launches are asynchronous on `stream`; no hidden synchronisation except in the
+ *     *_host entry points, which say so
+ *   - kernels read the model's parameters IN PLACE through the pointers below (no copies), so
+ *     in-place edits of the dense weights (the reference's pruner, model/DeepFMs.py:660-673)
+ *     are visible to the next call; only the bf16 MLP image made by dfw_pack_mlp_bf16 and the
+ *     CSR image made by dfw_csr_* are derived data
+ */
+#ifndef DEEPFWFM_B200_H
+#define DEEPFWFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFW_ABI_VERSION 1
+#define DFW_MAX_DEPTH 8
+#define DFW_MAX_FIELDS 64
+#define DFW_MAX_K 32
+#define DFW_MAX_RANKS 8
+
+/* error codes (negative) */
+#define DFW_E_ARG (-1)       /* null pointer / bad size                         */
+#define DFW_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for  */
+#define DFW_E_ABI (-3)       /* struct size / version mismatch                  */
+#define DFW_E_NODEVICE (-4)  /* no sm_100 device: there is NO CPU fallback      */
+#define DFW_E_WORKSPACE (-5) /* workspace too small                             */
+
+/* dfw_model.flags */
+#define DFW_USE_FWFM   (1u << 0) /* field_cov weights; else FM (all pairs weight 1)  model/DeepFMs.py:353-367 */
+#define DFW_USE_FWLW   (1u << 1) /* first order = <E_f, fwfm_linear_f>              model/DeepFMs.py:338-347 */
+#define DFW_USE_LW     (1u << 2) /* first order projected by fm_1st                 model/DeepFMs.py:445-450 */
+#define DFW_USE_DEEP   (1u << 3) /* MLP term                                        model/DeepFMs.py:395-436 */
+#define DFW_CHECK_INDEX (1u << 8) /* out-of-range Xi sets *err_word (and reads row 0) instead of UB */
+
+/* qr_op of a table (model/QREmbeddingBag.py:167-172) */
+#define DFW_TABLE_PLAIN 0
+#define DFW_TABLE_QR_MULT 1
+#define DFW_TABLE_QR_ADD 2
+
+/* precision selector of dfw_forward */
+#define DFW_PREC_FP32 0      /* CUDA-core fp32 MLP: the 1e-5 parity path                  */
+#define DFW_PREC_BF16 1      /* tcgen05 bf16 MLP, fp32 accumulate: the looser-bound path  */
+#define DFW_PREC_FP32_CSR 2  /* fp32 CSR MLP for magnitude-pruned weights                 */
+
+/* One embedding field (reference: one entry of fm_2nd_embeddings / fm_1st_embeddings,
+ * model/DeepFMs.py:197-210, 1066-1091).  An array of F of these lives in DEVICE memory.
+ * Rank-sharded tables use w2_shard[]: row i lives on rank i % n_ranks at local
+ * row i / n_ranks; entries are peer-mapped device pointers (dfw_ipc_*).                      */
+typedef struct dfw_field_desc {
+    const float* w2;      /* (rows, K) second-order table, or quotient table (ceil(rows/c), K) */
+    const float* w2_r;    /* (c, K) remainder table for QR, else NULL                          */
+    const float* w1;      /* (rows, 1) first-order table / quotient table, NULL with USE_FWLW  */
+    const float* w1_r;    /* (c, 1) first-order remainder table for QR, else NULL              */
+    int64_t rows;         /* number of categories n_f: valid indices are [0, rows)            */
+    int32_t collisions;   /* QR c (>= 1); 1 for a plain table                                 */
+    int32_t qr_op;        /* DFW_TABLE_* of w2                                                */
+    int32_t qr1_op;       /* DFW_TABLE_* of w1                                                */
+    int32_t n_ranks;      /* 0/1: w2 is local; >1: use w2_shard[rank]                          */
+    const float* w2_shard[DFW_MAX_RANKS];
+} dfw_field_desc;
+
+/* CSR image of one pruned Linear layer (row = output neuron).  Built by dfw_csr_build. */
+typedef struct dfw_csr {
+    const int32_t* row_ptr; /* (out+1)                 */
+    const int32_t* col;     /* (nnz) input index       */
+    const float* val;       /* (nnz)                   */
+    int32_t nnz;
+    int32_t max_row_nnz;
+} dfw_csr;
+
+/* Everything `forward` reads, by pointer.  Filled by the host, passed by pointer (host memory). */
+typedef struct dfw_model {
+    uint32_t struct_bytes;          /* sizeof(dfw_model), checked                            */
+    uint32_t abi_version;           /* DFW_ABI_VERSION                                       */
+    uint32_t flags;                 /* DFW_USE_*                                             */
+    int32_t field_size;             /* F                                                     */
+    int32_t numerical;              /* num: fields [0,num) are one-row tables scaled by Xv   */
+    int32_t embedding_size;         /* K                                                     */
+    int32_t depth;                  /* h_depth                                               */
+    int32_t widths[DFW_MAX_DEPTH];  /* hidden widths                                         */
+    const dfw_field_desc* fields;   /* DEVICE array [F]                                      */
+    const float* fwfm_linear;       /* (F, K)  fwfm_linear.weight        or NULL             */
+    const float* fm_1st;            /* (F)     fm_1st.weight             or NULL             */
+    const float* field_cov;         /* (F, F)  field_cov.weight          or NULL (FM)        */
+    const float* bias;              /* (1)     bias                                          */
+    const float* W[DFW_MAX_DEPTH];  /* net_1_linear_l.weight (out, in) row-major fp32        */
+    const float* b[DFW_MAX_DEPTH];  /* net_1_linear_l.bias                                   */
+    const float* fc;                /* (N) net_1_fc.weight                                   */
+    const void* Wbf16[DFW_MAX_DEPTH]; /* dfw_pack_mlp_bf16 image of W[l], or NULL            */
+    dfw_csr csr[DFW_MAX_DEPTH];     /* dfw_csr_build image of W[l] (row_ptr NULL if absent)  */
+} dfw_model;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dfw_version(void);
+const char* dfw_last_error_string(void);
+/* 0 if device `ordinal` is sm_100; DFW_E_NODEVICE otherwise (callers must fail loudly). */
+int dfw_check_device(int ordinal);
+/* sizeof of the ABI structs as the library was compiled: 0 dfw_model, 1 dfw_field_desc, 2 dfw_csr. */
+size_t dfw_struct_bytes(int which);
+/* Number of kernels this library has launched in the calling process (bench's gpu_launches). */
+int64_t dfw_launch_count(void);
+
+/* ---- stage 1: gather + Xv scale + first order + FM/FwFM second order ---------------------
+ * Replaces model/DeepFMs.py:297-367 (and 445-450, the use_lw projection) and
+ * model/QREmbeddingBag.py:156-174.
+ *   xi   (B, F-num, 1) int64, element strides given (non-contiguous views accepted)
+ *   xv   (B, num) fp32, element strides given
+ *   E_out      (B, ldE) fp32 or NULL : E[b, f*K+k], field-major == torch.cat(list, 1) (:398); columns
+ *              [F*K, ldE) are zero-filled
+ *   E_bf16_out (B, ldEb) bf16 or NULL: same values rounded to bf16 (operand of the tcgen05 MLP)
+ *   shallow_out (B) fp32: sum(first) + sum(second) + bias   (the non-deep part of :458/:463)
+ *   err_word   int32 device word, set to 1+field on an out-of-range index when DFW_CHECK_INDEX
+ */
+int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
+                   const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B,
+                   float* E_out, int64_t ldE, void* E_bf16_out, int64_t ldEb,
+                   float* shallow_out, int32_t* err_word, int32_t my_rank, void* stream);
+
+/* ---- stage 2: deep MLP + total + optional sigmoid -----------------------------------------
+ * Replaces model/DeepFMs.py:408-436 and the sum at :458; `prob_out` fuses the sigmoid every
+ * reference caller applies next (model/DeepFMs.py:777, 861, 872).
+ *   X (B, ldX) fp32 (= E_out), shallow (B) or NULL, logits_out (B), prob_out (B) or NULL
+ *   workspace: dfw_mlp_workspace_bytes(m, B, precision) bytes of device memory, 256-byte aligned
+ */
+size_t dfw_mlp_workspace_bytes(const dfw_model* m, int64_t B, int precision);
+int dfw_mlp_fp32(const dfw_model* m, const float* X, int64_t ldX, int64_t B, const float* shallow,
+                 void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
+                 void* stream);
+int dfw_mlp_csr(const dfw_model* m, const float* X, int64_t ldX, int64_t B, const float* shallow,
+                void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
+                void* stream);
+/* tcgen05 / TMA path.  Xb (B_pad, ldXb) bf16 where B_pad = B rounded up to 128 rows of readable
+ * memory; weights from dfw_pack_mlp_bf16. */
+int dfw_mlp_bf16(const dfw_model* m, const void* Xb, int64_t ldXb, int64_t B, const float* shallow,
+                 void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
+                 void* stream);
+/* no-deep models: logits = shallow, prob = sigmoid(shallow) */
+int dfw_finish_shallow(const float* shallow, int64_t B, float* logits_out, float* prob_out, void* stream);
+
+/* ---- derived weight images ---------------------------------------------------------------- */
+/* bf16 image of one Linear weight (out, in) fp32 -> (out_pad, in_pad) bf16, zero padded; sizes via
+ * dfw_pack_mlp_bf16_bytes.  Runs on the device (no host sync). */
+size_t dfw_pack_mlp_bf16_bytes(int32_t out_dim, int32_t in_dim);
+int dfw_pack_mlp_bf16(const float* W, int32_t out_dim, int32_t in_dim, void* dst, void* stream);
+/* CSR image of one pruned Linear weight.  Two device passes: count (fills row_ptr, returns nnz through
+ * a device word the caller reads) and fill.  `row_ptr` has out_dim+1 entries. */
+int dfw_csr_count(const float* W, int32_t out_dim, int32_t in_dim, int32_t* row_ptr, void* stream);
+int dfw_csr_fill(const float* W, int32_t out_dim, int32_t in_dim, const int32_t* row_ptr,
+                 int32_t* col, float* val, void* stream);
+
+/* ---- whole forward -------------------------------------------------------------------------
+ * Replaces the body of DeepFMs.forward (model/DeepFMs.py:285-469).  Device inputs.
+ *   workspace: dfw_forward_workspace_bytes(m, B, precision) bytes
+ */
+size_t dfw_forward_workspace_bytes(const dfw_model* m, int64_t B, int precision);
+int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
+                const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
+                void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
+                int32_t* err_word, void* stream);
+/* Same with HOST inputs/outputs (what eval_by_batch / predict_proba do around forward,
+ * model/DeepFMs.py:771-777): H2D of xi/xv (contiguous) into the staging area at the start of the
+ * workspace, forward, sigmoid, D2H of `prob_host` and/or `logits_host`, then SYNCHRONISES `stream`.
+ * Host buffers should be pinned.  workspace: dfw_forward_host_workspace_bytes. */
+size_t dfw_forward_host_workspace_bytes(const dfw_model* m, int64_t B, int precision);
+int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t B,
+                     int precision, void* workspace, size_t workspace_bytes, float* logits_host,
+                     float* prob_host, void* stream);
+
+/* ---- multi-GPU: row-sharded tables ------------------------------------------- */
+/* cudaMalloc'ed shard storage that can be exported to peers of the same node. */
+int dfw_shard_alloc(size_t bytes, void** dev_ptr);
+int dfw_shard_free(void* dev_ptr);
+int dfw_ipc_export(const void* dev_ptr, uint8_t handle_out[64]);
+int dfw_ipc_import(const uint8_t handle[64], void** peer_ptr);
+int dfw_ipc_close(void* peer_ptr);
+/* Build this rank's shard of a table: dst[r, :] = src[r * n_ranks + rank, :]. */
+int dfw_shard_rows(const float* src, int64_t rows, int32_t width, int32_t rank, int32_t n_ranks,
+                   float* dst, void* stream);
+/* NCCL-exchange variant: owner-side gather of requested rows into a send buffer.
+ *   req (n) int64 global row ids all owned by this rank -> out (n, width) */
+int dfw_gather_rows(const float* shard, int64_t shard_rows, int32_t width, const int64_t* req, int64_t n,
+                    int32_t n_ranks, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPFWFM_B200_H */

@@ -152,7 +152,31 @@ def tiny_criteo():
     print(f"tiny_criteo.npz size={os.path.getsize(p) / 1024:.0f} KiB")
 
 
+def ctor_parity():
+    """Checksums of the reference's parameters right after construction and after init_weights()
+    (CPU, fixed seed): the drop-in module must reproduce them with the same RNG call order."""
+    out = {}
+    variants = {
+        "plain": dict(use_fm=False, use_fwfm=True, use_deep=True, use_lw=True, deep_nodes=32),
+        "fwlw_bag": dict(use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, embedding_bag=True, deep_nodes=32),
+        "qr": dict(use_fm=False, use_fwfm=True, use_deep=True, qr_flag=1, qr_collisions=4, deep_nodes=32),
+        "fm": dict(use_fm=True, use_fwfm=False, use_deep=False),
+    }
+    for tag, kw in variants.items():
+        m = RefDeepFMs(39, SMALL, use_cuda=False, random_seed=42, logger=LOG, **kw)
+        out[f"{tag}::kw"] = json.dumps(kw)
+        out[f"{tag}::ctor"] = synth.weights_checksum({k: v.numpy() for k, v in m.state_dict().items()})
+        m.init_weights()
+        out[f"{tag}::init"] = synth.weights_checksum({k: v.numpy() for k, v in m.state_dict().items()})
+        out[f"{tag}::names"] = json.dumps({k: list(v.shape) for k, v in m.state_dict().items()})
+    np.savez_compressed(os.path.join(HERE, "ctor_parity.npz"), **out)
+    print("ctor_parity.npz written")
+
+
 def main():
+    ctor_parity()
+    if "--ctor-only" in sys.argv:
+        return
     C = lambda **kw: PathConfig(39, SMALL, **kw)  # noqa: E731
     fw = dict(use_fm=False, use_fwfm=True)
     cases = [

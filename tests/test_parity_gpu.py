@@ -1,0 +1,247 @@
+"""Parity of the CUDA path (through the C ABI) with the golden fixtures and the oracle.  Needs a B200.
+
+Bars: gathered rows bit-exact; fp32 logits within 1e-5 * max|logit_ref|; the pruned
+CSR path under the same fp32 bound; the bf16 tensor path within 5e-4 * max|logit_ref|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, load_case, load_tiny, tiny_weights, logit_tol
+from oracle import closed_form, prune, synth
+from oracle.config import PathConfig
+from test_module_cpu import build
+
+pytestmark = pytest.mark.gpu
+FP32_REL = 1e-5
+BF16_REL = 5e-4
+
+
+def to_cuda(cfg, weights, **kw):
+    m = build(cfg, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+    return m.cuda().eval()
+
+
+def run(m, Xi, Xv):
+    with torch.no_grad():
+        return m(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda()).cpu().numpy()
+
+
+def test_library_loaded_and_device_ok():
+    from xsdeepfwfm_deprecated_b200 import _lib
+    _lib.require_device(0)
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_logits_fp32(name):
+    c = load_case(name)
+    m = to_cuda(c["cfg"], c["weights"])
+    got = run(m, c["Xi"], c["Xv"])
+    assert got.shape == c["logits"].shape and got.dtype == np.float32
+    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL)
+    ref64 = closed_form.forward(c["cfg"], c["weights"], c["Xi"], c["Xv"])["logit"]
+    assert np.abs(got - ref64).max() <= logit_tol(ref64, FP32_REL)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_gathered_block_bit_exact(name):
+    c = load_case(name)
+    m = to_cuda(c["cfg"], c["weights"])
+    E, shallow = m.gathered_block(torch.from_numpy(c["Xi"]).cuda(), torch.from_numpy(c["Xv"]).cuda())
+    assert np.array_equal(E.cpu().numpy(), c["E"])          # rows / Xv products exactly as the reference's
+    o = closed_form.forward(c["cfg"], c["weights"], c["Xi"], c["Xv"])
+    want = o["first"] + o["second"] + float(c["weights"]["bias"][0])
+    assert np.abs(shallow.cpu().numpy() - want).max() <= logit_tol(o["logit"], FP32_REL)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if load_case(n)["cfg"].use_deep])
+def test_golden_logits_csr(name):
+    c = load_case(name)
+    m = to_cuda(c["cfg"], c["weights"], precision="fp32_csr")
+    got = run(m, c["Xi"], c["Xv"])
+    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if load_case(n)["cfg"].use_deep])
+def test_golden_logits_bf16(name):
+    c = load_case(name)
+    m = to_cuda(c["cfg"], c["weights"], precision="bf16")
+    try:
+        got = run(m, c["Xi"], c["Xv"])
+    except Exception as e:
+        if "not built" in str(e):
+            pytest.skip("bf16 tensor path not built yet")
+        raise
+    # the shallow part stays fp32; only the deep term carries bf16 operand rounding
+    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], BF16_REL) + 2e-2 * np.abs(
+        closed_form.forward(c["cfg"], c["weights"], c["Xi"], c["Xv"])["deep"]).max()
+
+
+def test_sigmoid_epilogue_and_prob():
+    c = load_case("deepfwfm_fwlw")
+    m = to_cuda(c["cfg"], c["weights"])
+    with torch.no_grad():
+        logits, prob = m(torch.from_numpy(c["Xi"]).cuda(), torch.from_numpy(c["Xv"]).cuda(), return_prob=True)
+    want = torch.sigmoid(logits)
+    assert torch.allclose(prob, want, atol=2e-7, rtol=1e-6)
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 1000])
+def test_ragged_batches(B):
+    c = load_case("deepfwfm_fwlw")
+    cfg = c["cfg"]
+    Xi, Xv = synth.make_inputs(cfg, B, seed=B)
+    m = to_cuda(cfg, c["weights"])
+    got = run(m, Xi, Xv)
+    ref = closed_form.forward(cfg, c["weights"], Xi, Xv)["logit"]
+    assert got.shape == (B,)
+    assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL)
+
+
+def test_empty_batch():
+    c = load_case("deepfwfm_fwlw")
+    m = to_cuda(c["cfg"], c["weights"])
+    out = m(torch.empty(0, 26, 1, dtype=torch.int64, device="cuda"), torch.empty(0, 13, device="cuda"))
+    assert out.shape == (0,)
+
+
+def test_non_contiguous_views():
+    c = load_case("deepfwfm_fwlw")
+    m = to_cuda(c["cfg"], c["weights"])
+    Xi = torch.from_numpy(c["Xi"]).cuda()
+    Xv = torch.from_numpy(c["Xv"]).cuda()
+    B = Xi.shape[0]
+    big_i = torch.zeros(B, 2 * 26, 2, dtype=torch.int64, device="cuda")
+    big_i[:, ::2, :1] = Xi
+    big_v = torch.zeros(2 * B, 2 * 13, device="cuda")
+    big_v[::2, ::2] = Xv
+    vi, vv = big_i[:, ::2, :1], big_v[::2, ::2]
+    assert not vi.is_contiguous() and not vv.is_contiguous()
+    with torch.no_grad():
+        a, b = m(Xi, Xv), m(vi, vv)
+    assert torch.equal(a, b)
+
+
+def test_index_out_of_range_is_a_defined_error():
+    c = load_case("fwfm")
+    m = to_cuda(c["cfg"], c["weights"], check_index=True)
+    Xi = torch.from_numpy(c["Xi"]).cuda().clone()
+    Xi[3, 5, 0] = c["cfg"].feature_sizes[13 + 5]          # one past the end
+    with pytest.raises(IndexError, match="field 18"):
+        m(Xi, torch.from_numpy(c["Xv"]).cuda())
+    Xi[3, 5, 0] = -1
+    with pytest.raises(IndexError):
+        m(Xi, torch.from_numpy(c["Xv"]).cuda())
+
+
+def test_in_place_pruning_is_seen_without_repack():
+    """The reference prunes with param.data[mask] = 0 (model/DeepFMs.py:660-673); the dense kernels read the
+    live parameters, so the very next forward must reflect it."""
+    c = load_case("deepfwfm_fwlw")
+    m = to_cuda(c["cfg"], c["weights"])
+    before = run(m, c["Xi"], c["Xv"])
+    pruned = prune.one_shot_prune(c["weights"], 0.9, 0.444, 1.0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            p.data[torch.from_numpy(pruned[k] == 0).cuda() & (p.data != 0)] = 0
+    after = run(m, c["Xi"], c["Xv"])
+    ref = closed_form.forward(c["cfg"], pruned, c["Xi"], c["Xv"])["logit"]
+    assert np.abs(after - ref).max() <= logit_tol(ref, FP32_REL)
+    assert np.abs(after - before).max() > 1e-3
+
+
+def test_pruned_pair_list_and_csr_agree_with_dense():
+    c = load_case("pruned")
+    dense = run(to_cuda(c["cfg"], c["weights"]), c["Xi"], c["Xv"])
+    csr = run(to_cuda(c["cfg"], c["weights"], precision="fp32_csr"), c["Xi"], c["Xv"])
+    assert np.abs(dense - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL)
+    assert np.abs(csr - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL)
+    # R given by the reference's own pruned-R dump pattern: half the entries exactly zero
+    W = c["weights"]["field_cov.weight"]
+    live = np.count_nonzero(np.triu(0.5 * (W + W.T), 1))
+    assert live < 741 // 6          # this fixture exercises the compacted pair-list walk
+
+
+def test_init_weights_rebinding_is_noticed():
+    c = load_case("deepfwfm_lw")
+    m = to_cuda(c["cfg"], c["weights"])
+    a = run(m, c["Xi"], c["Xv"])
+    torch.manual_seed(5)
+    m.init_weights()
+    m.eval()
+    b = run(m, c["Xi"], c["Xv"])
+    w = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    ref = closed_form.forward(c["cfg"], w, c["Xi"], c["Xv"])["logit"]
+    assert np.abs(b - ref).max() <= logit_tol(ref, FP32_REL)
+    assert np.abs(a - b).max() > 1e-3
+
+
+@pytest.mark.parametrize("tag", ["lw1", "lw0", "deep_fwlw"])
+def test_config1_tiny_criteo_eval_by_batch(tag):
+    """BASELINE config 1: all 10,000 bundled rows through eval_by_batch (8192 + ragged 1808)."""
+    t = load_tiny()
+    v = t["variants"][tag]
+    m = to_cuda(v["cfg"], tiny_weights(v))
+    loss, auc, prauc, rce = m.eval_by_batch(t["Xi"], t["Xv"], t["y"], len(t["y"]))
+    ref_loss, ref_auc, ref_prauc, ref_rce = v["metrics"]
+    assert abs(auc - ref_auc) <= 1e-6
+    assert abs(prauc - ref_prauc) <= 1e-5
+    assert abs(loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    got = m.predict_proba_host(t["Xi"], t["Xv"], want_logits=True)[1]
+    assert np.abs(got - v["logits"]).max() <= logit_tol(v["logits"], FP32_REL)
+
+
+def test_config2_full_size_batch_4096():
+    """BASELINE config 2 at full size: paper-Criteo cardinalities, B = 4096, dense DeepFwFM + fwlw."""
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    Xi, Xv = synth.make_inputs(cfg, 4096, seed=0)
+    ref = closed_form.forward(cfg, w, Xi, Xv)
+    m = to_cuda(cfg, w)
+    got = run(m, Xi, Xv)
+    assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], FP32_REL)
+    E, _ = m.gathered_block(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda())
+    assert np.array_equal(E.cpu().numpy(), ref["E32"])
+    # size-independent properties: batch-order equivariance and sample independence
+    perm = np.random.default_rng(0).permutation(4096)
+    got_p = run(m, Xi[perm], Xv[perm])
+    assert np.array_equal(got_p, got[perm])
+    assert np.array_equal(run(m, Xi[:100], Xv[:100]), got[:100])
+
+
+def test_config3_pruned_full_size():
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = prune.one_shot_prune(synth.make_weights(cfg, seed=42), 0.9, 0.444, 1.0)
+    Xi, Xv = synth.make_inputs(cfg, 4096, seed=3, dist="zipf")
+    ref = closed_form.forward(cfg, w, Xi, Xv)["logit"]
+    for precision in ("fp32", "fp32_csr"):
+        got = run(to_cuda(cfg, w, precision=precision), Xi, Xv)
+        assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL), precision
+
+
+def test_config4_qr_full_cardinality_tables():
+    """QR (mult, c=4, threshold 200) on the un-thresholded Kaggle cardinalities: 338 MB of tables."""
+    cfg = PathConfig(39, synth.CRITEO_KAGGLE, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True,
+                     qr_flag=1, qr_collisions=4, qr_threshold=200, deep_nodes=64)
+    w = synth.make_weights(cfg, seed=11)
+    Xi, Xv = synth.make_inputs(cfg, 2048, seed=4)
+    ref = closed_form.forward(cfg, w, Xi, Xv)
+    m = to_cuda(cfg, w)
+    got = run(m, Xi, Xv)
+    assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], FP32_REL)
+    E, _ = m.gathered_block(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda())
+    assert np.array_equal(E.cpu().numpy(), ref["E32"])
+
+
+def test_standalone_qr_lookup_bit_exact():
+    from xsdeepfwfm_deprecated_b200.model import QREmbeddingBag
+    torch.manual_seed(0)
+    for op, c in (("mult", 4), ("add", 7)):
+        t = QREmbeddingBag(100003, 10, c, operation=op, mode="sum").cuda()
+        idx = torch.randint(0, 100003, (777, 1), device="cuda")
+        got = t(idx)
+        q, r = idx[:, 0] // c, idx[:, 0] % c
+        want = t.weight_q[q] * t.weight_r[r] if op == "mult" else t.weight_q[q] + t.weight_r[r]
+        assert torch.equal(got, want.detach())

@@ -1,0 +1,224 @@
+// C-ABI glue of libdeepfwfm_sm100a: error strings, device check, whole-forward entry points, shard helpers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "dfw_common.cuh"
+
+namespace dfw {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct FwdLayout {
+    int ldE, ldEb;
+    int64_t Bp;
+    size_t oErr, oE, oEb, oShallow, oMlp, total;
+};
+
+static FwdLayout fwd_layout(const dfw_model* m, int64_t B, int precision) {
+    FwdLayout L;
+    const int FK = m->field_size * m->embedding_size;
+    L.ldE = (FK + 3) / 4 * 4;
+    L.ldEb = (FK + 7) / 8 * 8;
+    L.Bp = (B + 127) / 128 * 128;
+    const bool deep = m->flags & DFW_USE_DEEP;
+    size_t o = 0;
+    L.oErr = o; o += 256;
+    L.oE = o;   if (deep && precision != DFW_PREC_BF16) o += align_up((size_t)L.Bp * L.ldE * sizeof(float), 256);
+    L.oEb = o;  if (deep && precision == DFW_PREC_BF16) o += align_up((size_t)L.Bp * L.ldEb * 2, 256);
+    L.oShallow = o; o += align_up((size_t)L.Bp * sizeof(float), 256);
+    L.oMlp = o; o += deep ? align_up(dfw_mlp_workspace_bytes(m, B, precision), 256) : 0;
+    L.total = o;
+    return L;
+}
+
+__global__ void shard_rows_kernel(const float* __restrict__ src, int64_t rows, int width, int rank, int n_ranks,
+                                  float* __restrict__ dst) {
+    const int64_t local_rows = (rows - rank + n_ranks - 1) / n_ranks;
+    const int64_t total = local_rows * width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / width;
+        const int c = (int)(i - r * width);
+        dst[i] = src[(r * n_ranks + rank) * width + c];
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ shard, int64_t shard_rows, int width,
+                                   const int64_t* __restrict__ req, int64_t n, int n_ranks, float* __restrict__ out) {
+    const int64_t total = n * width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / width;
+        const int c = (int)(i - r * width);
+        int64_t local = req[r] / n_ranks;
+        if (local < 0 || local >= shard_rows) local = 0;
+        out[i] = __ldg(shard + local * width + c);
+    }
+}
+
+}  // namespace dfw
+
+using namespace dfw;
+
+extern "C" int dfw_version(void) { return DFW_ABI_VERSION; }
+extern "C" const char* dfw_last_error_string(void) { return g_err; }
+extern "C" size_t dfw_struct_bytes(int which) {
+    return which == 0 ? sizeof(dfw_model) : which == 1 ? sizeof(dfw_field_desc) : which == 2 ? sizeof(dfw_csr) : 0;
+}
+extern "C" int64_t dfw_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int dfw_check_device(int ordinal) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return DFW_E_NODEVICE;
+    }
+    DFW_REQUIRE(ordinal >= 0 && ordinal < n, DFW_E_ARG, "device ordinal %d outside [0,%d)", ordinal, n);
+    cudaDeviceProp prop;
+    DFW_CUDA_OK(cudaGetDeviceProperties(&prop, ordinal));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libdeepfwfm_sm100a carries sm_100a code only", ordinal, prop.major, prop.minor);
+        return DFW_E_NODEVICE;
+    }
+    return 0;
+}
+
+extern "C" size_t dfw_forward_workspace_bytes(const dfw_model* m, int64_t B, int precision) {
+    if (!m || B <= 0) return 256;
+    return fwd_layout(m, B, precision).total;
+}
+
+extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
+                           const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
+                           void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
+                           int32_t* err_word, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");
+    if (B == 0) return 0;
+    DFW_REQUIRE(logits_out || prob_out, DFW_E_ARG, "no output requested");
+    DFW_REQUIRE(precision == DFW_PREC_FP32 || precision == DFW_PREC_BF16 || precision == DFW_PREC_FP32_CSR,
+                DFW_E_ARG, "unknown precision %d", precision);
+    const FwdLayout L = fwd_layout(m, B, precision);
+    DFW_REQUIRE(workspace && workspace_bytes >= L.total, DFW_E_WORKSPACE, "forward workspace too small: %zu < %zu",
+                workspace_bytes, L.total);
+    DFW_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, DFW_E_ARG, "workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(workspace);
+    const bool deep = m->flags & DFW_USE_DEEP;
+    float* E = (deep && precision != DFW_PREC_BF16) ? reinterpret_cast<float*>(ws + L.oE) : nullptr;
+    void* Eb = (deep && precision == DFW_PREC_BF16) ? static_cast<void*>(ws + L.oEb) : nullptr;
+    float* shallow = reinterpret_cast<float*>(ws + L.oShallow);
+    if (!err_word) err_word = reinterpret_cast<int32_t*>(ws + L.oErr);
+    if (int rc = dfw_embed_fwfm(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, E, L.ldE, Eb, L.ldEb,
+                                shallow, err_word, 0, stream))
+        return rc;
+    if (!deep) return dfw_finish_shallow(shallow, B, logits_out, prob_out, stream);
+    void* mws = ws + L.oMlp;
+    const size_t mbytes = workspace_bytes - L.oMlp;
+    if (precision == DFW_PREC_BF16) return dfw_mlp_bf16(m, Eb, L.ldEb, B, shallow, mws, mbytes, logits_out, prob_out, stream);
+    if (precision == DFW_PREC_FP32_CSR) return dfw_mlp_csr(m, E, L.ldE, B, shallow, mws, mbytes, logits_out, prob_out, stream);
+    return dfw_mlp_fp32(m, E, L.ldE, B, shallow, mws, mbytes, logits_out, prob_out, stream);
+}
+
+namespace {
+struct HostLayout { size_t oXi, oXv, oLogit, oProb, oFwd, total; };
+HostLayout host_layout(const dfw_model* m, int64_t B, int precision) {
+    HostLayout H;
+    const int C = m->field_size - m->numerical;
+    size_t o = 0;
+    H.oXi = o;    o += align_up((size_t)B * (C > 0 ? C : 1) * sizeof(int64_t), 256);
+    H.oXv = o;    o += align_up((size_t)B * (m->numerical > 0 ? m->numerical : 1) * sizeof(float), 256);
+    H.oLogit = o; o += align_up((size_t)B * sizeof(float), 256);
+    H.oProb = o;  o += align_up((size_t)B * sizeof(float), 256);
+    H.oFwd = o;   o += fwd_layout(m, B, precision).total;
+    H.total = o;
+    return H;
+}
+}  // namespace
+
+extern "C" size_t dfw_forward_host_workspace_bytes(const dfw_model* m, int64_t B, int precision) {
+    if (!m || B <= 0) return 256;
+    return host_layout(m, B, precision).total;
+}
+
+extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t B,
+                                int precision, void* workspace, size_t workspace_bytes, float* logits_host,
+                                float* prob_host, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    if (B <= 0) return 0;
+    DFW_REQUIRE(logits_host || prob_host, DFW_E_ARG, "no output requested");
+    const HostLayout H = host_layout(m, B, precision);
+    DFW_REQUIRE(workspace && workspace_bytes >= H.total, DFW_E_WORKSPACE, "host-forward workspace too small: %zu < %zu",
+                workspace_bytes, H.total);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    const int C = m->field_size - m->numerical, num = m->numerical;
+    int64_t* xi = reinterpret_cast<int64_t*>(ws + H.oXi);
+    float* xv = reinterpret_cast<float*>(ws + H.oXv);
+    float* logit = reinterpret_cast<float*>(ws + H.oLogit);
+    float* prob = reinterpret_cast<float*>(ws + H.oProb);
+    if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host, (size_t)B * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host, (size_t)B * num * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, B, precision, ws + H.oFwd, workspace_bytes - H.oFwd,
+                             logits_host ? logit : nullptr, prob_host ? prob : nullptr, nullptr, stream))
+        return rc;
+    if (logits_host) DFW_CUDA_OK(cudaMemcpyAsync(logits_host, logit, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (prob_host) DFW_CUDA_OK(cudaMemcpyAsync(prob_host, prob, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DFW_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- multi-GPU helpers -------------------------------------------------------------------------
+extern "C" int dfw_shard_alloc(size_t bytes, void** dev_ptr) {
+    DFW_REQUIRE(dev_ptr, DFW_E_ARG, "dev_ptr is NULL");
+    DFW_CUDA_OK(cudaMalloc(dev_ptr, bytes ? bytes : 256));
+    return 0;
+}
+extern "C" int dfw_shard_free(void* dev_ptr) {
+    if (dev_ptr) DFW_CUDA_OK(cudaFree(dev_ptr));
+    return 0;
+}
+extern "C" int dfw_ipc_export(const void* dev_ptr, uint8_t handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    DFW_REQUIRE(dev_ptr && handle_out, DFW_E_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    DFW_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+extern "C" int dfw_ipc_import(const uint8_t handle[64], void** peer_ptr) {
+    DFW_REQUIRE(handle && peer_ptr, DFW_E_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    DFW_CUDA_OK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int dfw_ipc_close(void* peer_ptr) {
+    if (peer_ptr) DFW_CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+extern "C" int dfw_shard_rows(const float* src, int64_t rows, int32_t width, int32_t rank, int32_t n_ranks,
+                              float* dst, void* stream) {
+    DFW_REQUIRE(src && dst && rows >= 0 && width > 0 && n_ranks > 0 && rank >= 0 && rank < n_ranks, DFW_E_ARG,
+                "bad shard_rows arguments");
+    if (rows == 0) return 0;
+    shard_rows_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, rows, width, rank, n_ranks, dst);
+    count_launch();
+    return check_launch("shard_rows_kernel");
+}
+extern "C" int dfw_gather_rows(const float* shard, int64_t shard_rows, int32_t width, const int64_t* req, int64_t n,
+                               int32_t n_ranks, float* out, void* stream) {
+    DFW_REQUIRE(shard && out && width > 0 && n_ranks > 0 && n >= 0, DFW_E_ARG, "bad gather_rows arguments");
+    if (n == 0) return 0;
+    DFW_REQUIRE(req, DFW_E_ARG, "req is NULL");
+    gather_rows_kernel<<<592, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(shard, shard_rows, width, req, n, n_ranks, out);
+    count_launch();
+    return check_launch("gather_rows_kernel");
+}
