@@ -153,7 +153,10 @@ embed_fwfm_kernel(const EmbedParams p) {
         const int nw = F * (int)(sizeof(dfw_field_desc) / 8);
         for (int i = tid; i < nw; i += nthreads) dst[i] = __ldg(src + i);
     }
-    if (fwlw) for (int i = tid; i < FK; i += nthreads) sWl[i] = __ldg(p.wl + i);
+    if (fwlw) {   // fwlw weights; with use_lw the per-field projection fm_1st[f] is folded in (model/DeepFMs.py:450)
+        const bool lw = p.flags & DFW_USE_LW;
+        for (int i = tid; i < FK; i += nthreads) sWl[i] = __ldg(p.wl + i) * (lw ? __ldg(p.fm1 + i / K) : 1.0f);
+    }
     if (tid == 0) sMisc[0] = 0;
     __syncthreads();   // descriptors visible (rows needed for the bounds check)
 

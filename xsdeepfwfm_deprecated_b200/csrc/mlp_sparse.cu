@@ -15,7 +15,7 @@
 
 namespace dfw {
 
-constexpr int CS_SAMPLES = 64, CS_WARPS = 16;
+constexpr int CS_WARPS = 16;
 
 struct CsrParams {
     int depth, in_dim;
@@ -28,8 +28,11 @@ struct CsrParams {
     int64_t B; int pitch;
 };
 
+// S = samples per lane: 2 (64-sample tile) when two activation tiles fit in shared memory, else 1.
+template <int S>
 __global__ void __launch_bounds__(CS_WARPS * 32, 1)
 csr_mlp_kernel(const CsrParams p) {
+    constexpr int CS_SAMPLES = 32 * S;
     extern __shared__ __align__(16) float smem[];
     float* tile[2] = {smem, smem + CS_SAMPLES * p.pitch};
     float* sRed = smem + 2 * CS_SAMPLES * p.pitch;          // [CS_WARPS][64]
@@ -52,7 +55,7 @@ csr_mlp_kernel(const CsrParams p) {
         const dfw_csr M = p.csr[l];
         const bool last = (l == p.depth - 1);
         const float* in0 = in + lane * pitch;
-        const float* in1 = in + (lane + 32) * pitch;
+        const float* in1 = in + (lane + (S > 1 ? 32 : 0)) * pitch;
         for (int n = warp; n < p.widths[l]; n += CS_WARPS) {
             const int beg = __ldg(M.row_ptr + n), end = __ldg(M.row_ptr + n + 1);
             float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
@@ -75,13 +78,13 @@ csr_mlp_kernel(const CsrParams p) {
                 d0 = fmaf(h0, w, d0); d1 = fmaf(h1, w, d1);
             } else {
                 out[lane * pitch + n] = h0;
-                out[(lane + 32) * pitch + n] = h1;
+                if (S > 1) out[(lane + 32) * pitch + n] = h1;
             }
         }
         __syncthreads();
     }
     sRed[warp * CS_SAMPLES + lane] = d0;
-    sRed[warp * CS_SAMPLES + lane + 32] = d1;
+    if (S > 1) sRed[warp * CS_SAMPLES + lane + 32] = d1;
     __syncthreads();
     if (threadIdx.x < CS_SAMPLES && threadIdx.x < nrows) {
         float z = 0.f;
@@ -171,14 +174,14 @@ extern "C" int dfw_mlp_csr(const dfw_model* m, const float* X, int64_t ldX, int6
     }
     p.fc = m->fc; p.X = X; p.ldX = ldX; p.shallow = shallow; p.logits = logits_out; p.prob = prob_out; p.B = B;
     p.pitch = wmax | 1;
-    const size_t smem = sizeof(float) * ((size_t)2 * CS_SAMPLES * p.pitch + CS_WARPS * CS_SAMPLES);
+    auto smem_for = [&](int samples) { return sizeof(float) * ((size_t)2 * samples * p.pitch + CS_WARPS * samples); };
+    const int S = smem_for(64) <= 227 * 1024 ? 2 : 1;
+    const size_t smem = smem_for(32 * S);
     DFW_REQUIRE(smem <= 227 * 1024, DFW_E_UNSUPPORTED, "CSR MLP: layer width %d needs %zu B of shared memory (> 227 KiB)", wmax, smem);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        DFW_CUDA_OK(cudaFuncSetAttribute(csr_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    csr_mlp_kernel<<<(unsigned)((B + CS_SAMPLES - 1) / CS_SAMPLES), CS_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    auto kern = S == 2 ? csr_mlp_kernel<2> : csr_mlp_kernel<1>;
+    DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int samples = 32 * S;
+    kern<<<(unsigned)((B + samples - 1) / samples), CS_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     count_launch();
     return check_launch("csr_mlp_kernel");
 }
