@@ -242,7 +242,7 @@ def run_ours(args):
         j = i % nb
         rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B,
                                 None if bf else E.data_ptr(), ldE, Eb.data_ptr() if bf else None, ldEb,
-                                shallow.data_ptr(), None, 0, sp)
+                                shallow.data_ptr(), None, sp)
         if rc:
             _lib.check(rc, "dfw_embed_fwfm")
 
@@ -254,13 +254,24 @@ def run_ours(args):
         if rc:
             _lib.check(rc, "dfw_mlp")
 
+    def graph_time(fn, n_it):
+        """ms per call of `fn`, replayed from a CUDA graph of n_it calls over distinct batches (device time only)."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(n_it):
+                fn(i)
+        with torch.cuda.stream(stream):
+            g.replay()
+            torch.cuda.synchronize(device)
+            return time_events(lambda i: g.replay(), 5, stream) / n_it
+
     with torch.cuda.stream(stream):
         for i in range(5):
             embed(i); mlp(i)
         torch.cuda.synchronize(device)
-        n_it = max(20, min(args.steps, 200))
-        t_embed = time_events(embed, n_it, stream)
-        t_mlp = time_events(mlp, n_it, stream)
+    n_it = 64
+    t_embed = graph_time(embed, n_it)
+    t_mlp = graph_time(mlp, n_it)
     pk = peaks()
     embed_bytes = ALG_BYTES_PER_SAMPLE * B + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4
     stage = {

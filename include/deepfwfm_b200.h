@@ -20,9 +20,10 @@
  *   - all launches are asynchronous on `stream`; no hidden synchronisation except in the
  *     *_host entry points, which say so
  *   - kernels read the model's parameters IN PLACE through the pointers below (no copies), so
- *     in-place edits of the dense weights (the reference's pruner, model/DeepFMs.py:660-673)
- *     are visible to the next call; only the bf16 MLP image made by dfw_pack_mlp_bf16 and the
- *     CSR image made by dfw_csr_* are derived data
+ *     in-place edits of the embedding tables and the fp32 MLP weights (the reference's pruner,
+ *     model/DeepFMs.py:660-666) are visible to the next call; derived data are the shallow image
+ *     (dfw_pack_shallow: field_cov, fwfm_linear, fm_1st, descriptors), the bf16 MLP image
+ *     (dfw_pack_mlp_bf16) and the CSR image (dfw_csr_*)
  */
 #ifndef DEEPFWFM_B200_H
 #define DEEPFWFM_B200_H
@@ -110,6 +111,7 @@ typedef struct dfw_model {
     const float* fc;                /* (N) net_1_fc.weight                                   */
     const void* Wbf16[DFW_MAX_DEPTH]; /* dfw_pack_mlp_bf16 image of W[l], or NULL            */
     dfw_csr csr[DFW_MAX_DEPTH];     /* dfw_csr_build image of W[l] (row_ptr NULL if absent)  */
+    const void* shallow_image;      /* dfw_pack_shallow image (DEVICE), or NULL: dfw_forward then packs per call */
 } dfw_model;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -136,7 +138,15 @@ int64_t dfw_launch_count(void);
 int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
                    const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B,
                    float* E_out, int64_t ldE, void* E_bf16_out, int64_t ldEb,
-                   float* shallow_out, int32_t* err_word, int32_t my_rank, void* stream);
+                   float* shallow_out, int32_t* err_word, void* stream);
+
+/* Shallow image: the batch-independent operands of stage 1 in the layout the kernel copies to shared memory --
+ * U = strict upper triangle of (field_cov + field_cov^T)/2 (model/DeepFMs.py:364; ones for FM), the compacted
+ * list of its non-zero pairs (pruned R, model/DeepFMs.py:667-673), fwfm_linear with fm_1st folded in, and the
+ * field descriptors.  Derived data: rebuild after field_cov / fwfm_linear / fm_1st / table pointers change.
+ * Runs on the device, no host synchronisation.  `image`: dfw_shallow_image_bytes(m) bytes, 16-byte aligned. */
+size_t dfw_shallow_image_bytes(const dfw_model* m);
+int dfw_pack_shallow(const dfw_model* m, void* image, void* stream);
 
 /* ---- stage 2: deep MLP + total + optional sigmoid -----------------------------------------
  * Replaces model/DeepFMs.py:408-436 and the sum at :458; `prob_out` fuses the sigmoid every

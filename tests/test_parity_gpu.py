@@ -136,9 +136,10 @@ def test_index_out_of_range_is_a_defined_error():
         m(Xi, torch.from_numpy(c["Xv"]).cuda())
 
 
-def test_in_place_pruning_is_seen_without_repack():
-    """The reference prunes with param.data[mask] = 0 (model/DeepFMs.py:660-673); the dense kernels read the
-    live parameters, so the very next forward must reflect it."""
+def test_in_place_pruning_is_seen_after_eval():
+    """The reference prunes with param.data[mask] = 0 inside fit() (model/DeepFMs.py:660-673) and every inference
+    entry point then calls eval() (model/DeepFMs.py:757): tables and MLP weights are read live, the shallow image
+    (field_cov / fwfm_linear) is rebuilt by eval()."""
     c = load_case("deepfwfm_fwlw")
     m = to_cuda(c["cfg"], c["weights"])
     before = run(m, c["Xi"], c["Xv"])
@@ -146,10 +147,26 @@ def test_in_place_pruning_is_seen_without_repack():
     with torch.no_grad():
         for k, p in m.named_parameters():
             p.data[torch.from_numpy(pruned[k] == 0).cuda() & (p.data != 0)] = 0
+    m.eval()
     after = run(m, c["Xi"], c["Xv"])
     ref = closed_form.forward(c["cfg"], pruned, c["Xi"], c["Xv"])["logit"]
     assert np.abs(after - ref).max() <= logit_tol(ref, FP32_REL)
     assert np.abs(after - before).max() > 1e-3
+
+
+def test_table_and_mlp_edits_are_live_without_any_repack():
+    c = load_case("deepfwfm_fwlw")
+    m = to_cuda(c["cfg"], c["weights"])
+    run(m, c["Xi"], c["Xv"])
+    w = {k: v.copy() for k, v in c["weights"].items()}
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "fm_2nd_embeddings" in k or "net_1_linear" in k:
+                w[k] = (w[k] * np.float32(0.5)).astype(np.float32)
+                p.data.mul_(0.5)
+    got = run(m, c["Xi"], c["Xv"])
+    ref = closed_form.forward(c["cfg"], w, c["Xi"], c["Xv"])["logit"]
+    assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL)
 
 
 def test_pruned_pair_list_and_csr_agree_with_dense():

@@ -42,7 +42,8 @@ class Model(C.Structure):
                 ("fields", C.c_void_p), ("fwfm_linear", C.c_void_p), ("fm_1st", C.c_void_p),
                 ("field_cov", C.c_void_p), ("bias", C.c_void_p),
                 ("W", C.c_void_p * DFW_MAX_DEPTH), ("b", C.c_void_p * DFW_MAX_DEPTH), ("fc", C.c_void_p),
-                ("Wbf16", C.c_void_p * DFW_MAX_DEPTH), ("csr", Csr * DFW_MAX_DEPTH)]
+                ("Wbf16", C.c_void_p * DFW_MAX_DEPTH), ("csr", Csr * DFW_MAX_DEPTH),
+                ("shallow_image", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/deepfwfm_b200.h declares
@@ -54,7 +55,9 @@ SYMBOLS = {
     "dfw_check_device": (C.c_int, [C.c_int]),
     "dfw_struct_bytes": (_sz, [C.c_int]),
     "dfw_launch_count": (_i64, []),
-    "dfw_embed_fwfm": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "dfw_embed_fwfm": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "dfw_shallow_image_bytes": (_sz, [_MP]),
+    "dfw_pack_shallow": (C.c_int, [_MP, _vp, _vp]),
     "dfw_mlp_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_mlp_fp32": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _vp, _vp]),
     "dfw_mlp_csr": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _vp, _sz, _vp, _vp, _vp]),

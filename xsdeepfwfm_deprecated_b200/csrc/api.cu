@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 struct FwdLayout {
     int ldE, ldEb;
     int64_t Bp;
-    size_t oErr, oE, oEb, oShallow, oMlp, total;
+    size_t oErr, oImg, oE, oEb, oShallow, oMlp, total;
 };
 
 static FwdLayout fwd_layout(const dfw_model* m, int64_t B, int precision) {
@@ -31,6 +31,7 @@ static FwdLayout fwd_layout(const dfw_model* m, int64_t B, int precision) {
     const bool deep = m->flags & DFW_USE_DEEP;
     size_t o = 0;
     L.oErr = o; o += 256;
+    L.oImg = o; if (!m->shallow_image) o += align_up(dfw_shallow_image_bytes(m), 256);
     L.oE = o;   if (deep && precision != DFW_PREC_BF16) o += align_up((size_t)L.Bp * L.ldE * sizeof(float), 256);
     L.oEb = o;  if (deep && precision == DFW_PREC_BF16) o += align_up((size_t)L.Bp * L.ldEb * 2, 256);
     L.oShallow = o; o += align_up((size_t)L.Bp * sizeof(float), 256);
@@ -116,8 +117,15 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     void* Eb = (deep && precision == DFW_PREC_BF16) ? static_cast<void*>(ws + L.oEb) : nullptr;
     float* shallow = reinterpret_cast<float*>(ws + L.oShallow);
     if (!err_word) err_word = reinterpret_cast<int32_t*>(ws + L.oErr);
+    dfw_model local;
+    if (!m->shallow_image) {   // "always fresh" mode: rebuild the shallow image from the live parameters per call
+        local = *m;
+        local.shallow_image = ws + L.oImg;
+        if (int rc = dfw_pack_shallow(m, ws + L.oImg, stream)) return rc;
+        m = &local;
+    }
     if (int rc = dfw_embed_fwfm(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, E, L.ldE, Eb, L.ldEb,
-                                shallow, err_word, 0, stream))
+                                shallow, err_word, stream))
         return rc;
     if (!deep) return dfw_finish_shallow(shallow, B, logits_out, prob_out, stream);
     void* mws = ws + L.oMlp;

@@ -3,18 +3,27 @@
 //
 // Replaces model/DeepFMs.py:297-367, 445-450 and model/QREmbeddingBag.py:156-174 of the reference.
 //
-// Layout of the work
-//   CTA  = 32 samples x K "k-lanes":  blockDim = (32, K);  thread (s, k) owns column k of sample s
-//   SMEM = the 32 x (F*K) embedding block of the CTA's samples (odd pitch -> conflict-free column
-//          reads), the symmetrised upper-triangular field matrix U (rows padded to float4), the
-//          fwlw weights, the field descriptors and the 32 x C indices
-//   phase A  descriptors, indices, U and fwlw weights -> SMEM                     (1 DRAM latency)
-//   phase B  all row segments of the CTA are requested before any is consumed     (1 DRAM latency)
-//            (32 samples x C rows x K floats, float2/float4 per request when K allows)
-//   phase C  E block streamed out (fp32 and/or bf16) while the FMAs of phase D run
-//   phase D  thread (s,k): e[f] = E[s][f][k] in registers;  t_i = sum_{j>i} U_ij e_j ;  acc += e_i t_i
-//            U comes from SMEM as broadcast LDS.128, so the inner loop is 4 FFMA per LDS
-//            when the field matrix is pruned (few live pairs) a compacted pair list is walked instead
+// Two kernels:
+//
+// pack_shallow_kernel (one CTA, run when the model is (re)packed, not per batch) builds the "shallow image":
+//   header | U = strict upper triangle of (R + R^T)/2 stored by columns, padded to float4 (FM: ones) |
+//   compacted list of live pairs (for pruned R) | fwlw weights with fm_1st folded in | field descriptors
+//
+// embed_fwfm_kernel, per batch:
+//   CTA  = 16 samples x K columns: thread t owns (sample t & 15, column t >> 4) in phase D
+//   SMEM = shallow image copy + the 16 x (F*K) embedding block of the CTA's samples (pitch = 2 mod 32
+//          floats: the column reads of a warp -- 16 samples x 2 columns -- hit 32 distinct banks, rows stay
+//          8-byte aligned) + the 16 x C indices + the 16 x num dense values
+//   phase A  indices / dense values (DRAM) into registers, shallow image (L2) by 16-byte cp.async  (1 latency)
+//   phase B  every stored row segment of the block goes global -> SMEM with 8-byte cp.async, all in flight
+//            together (one latency for the whole block, no register staging); the issuing thread then fixes
+//            up its own segments: quotient (*|+) remainder row for QR tables, times Xv for numeric fields --
+//            one fp32 operation each, exactly the reference's arithmetic
+//   phase C  E block streamed out (fp32 and/or bf16), coalesced
+//   phase D  thread (s,k): e[f] = E[s][f][k] in registers; for each column j: t_i += U_ij e_j (i < j) --
+//            F-1 independent accumulators, U read as broadcast LDS.128 -> 4 FFMA per LDS, no dependent
+//            chains; second = sum_i e_i t_i.  A pruned field matrix (few live pairs) is walked as the
+//            compacted pair list instead.
 //   phase E  fixed-order reduction over k -> shallow[b] = first + second + bias
 //
 // Bytes per sample the algorithm needs (Criteo, fwlw): 26*8 + 13*4 + 26*40 + 4 = 1304.
@@ -22,427 +31,516 @@
 
 namespace dfw {
 
-constexpr int kSamples = 32;  // samples per CTA (one warp lane each)
+constexpr int kS = 16;  // samples per CTA
 
 struct EmbedParams {
-    const dfw_field_desc* fields;
+    const unsigned char* image;
     const int64_t* xi; int64_t xi_sb, xi_sc;
     const float* xv; int64_t xv_sb, xv_sc;
-    const float* wl; const float* fm1; const float* cov; const float* bias;
+    const float* fm1; const float* bias;
     float* E; int64_t ldE; __nv_bfloat16* Eb; int64_t ldEb; float* shallow; int32_t* err;
-    int64_t B; int F, num, K; unsigned flags; int my_rank;
+    int64_t B; int F, num, K; unsigned flags;
 };
 
 struct PairEnt { uint32_t ij; float u; };  // ij = (i*K) | (j*K) << 16
+struct ImgHeader { int32_t live, n_list, any_qr, misaligned; };
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
-__host__ __device__ constexpr int urow_off(int F, int i) {
-    int o = 0;
-    for (int r = 0; r < i; ++r) o += pad4(F - 1 - r);
-    return o;
+// column j of the strict upper triangle holds U_0j .. U_(j-1)j, padded to a multiple of 4 floats:
+// offset = sum_{c=1}^{j-1} pad4(c) = 4 (m+1)(2m + r) with j-1 = 4m + r
+__host__ __device__ constexpr int ucol_off(int j) {
+    const int n = j - 1, m = n >> 2, r = n & 3;
+    return n <= 0 ? 0 : 4 * (m + 1) * (2 * m + r);
 }
-__host__ __device__ constexpr int usize(int F) { return urow_off(F, F - 1); }
+__host__ __device__ constexpr int usize(int F) { return ucol_off(F); }
+__host__ __device__ constexpr int e_pitch(int FK) { return FK + ((34 - (FK & 31)) & 31); }   // >= FK, == 2 mod 32
+__host__ __device__ constexpr size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
 
-struct SmemLayout {
-    int EP;       // pitch of the E block in floats (odd)
-    size_t oU, oPairs, oE, oWl, oPart, oFields, oIdx, oMisc, total;
-};
-__host__ __device__ inline SmemLayout smem_layout(int F, int K, int C) {
-    SmemLayout L;
-    const int FK = F * K;
-    L.EP = FK | 1;
+struct ImgLayout { size_t oHdr, oU, oPairs, oWl, oFields, total; };
+__host__ __device__ inline ImgLayout img_layout(int F, int K) {
+    ImgLayout L;
     size_t o = 0;
-    L.oU = o;      o += sizeof(float) * pad4(usize(F) + 4);
-    L.oPairs = o;  o += sizeof(PairEnt) * (size_t)(F * (F - 1) / 2);
-    o = (o + 15) & ~size_t(15);
-    L.oFields = o; o += sizeof(dfw_field_desc) * F;
-    L.oE = o;      o += sizeof(float) * kSamples * L.EP;
-    L.oWl = o;     o += sizeof(float) * FK;
-    L.oPart = o;   o += sizeof(float) * K * kSamples;
-    L.oIdx = o;    o += sizeof(int32_t) * kSamples * (C > 0 ? C : 1);
-    L.oMisc = o;   o += 16;
+    L.oHdr = o;    o += 16;
+    L.oU = o;      o += up16(sizeof(float) * (usize(F) + 4));
+    L.oPairs = o;  o += up16(sizeof(PairEnt) * (size_t)(F * (F - 1) / 2) + 8);
+    L.oWl = o;     o += up16(sizeof(float) * F * K);
+    L.oFields = o; o += up16(sizeof(dfw_field_desc) * F);
     L.total = o;
     return L;
 }
 
-template <int VEC> struct VecT;
-template <> struct VecT<1> { using T = float; };
-template <> struct VecT<2> { using T = float2; };
-template <> struct VecT<4> { using T = float4; };
-
-template <int VEC>
-__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
-    if ((reinterpret_cast<uintptr_t>(p) & (VEC * 4 - 1)) == 0) {
-        typename VecT<VEC>::T t = __ldg(reinterpret_cast<const typename VecT<VEC>::T*>(p));
-        const float* tf = reinterpret_cast<const float*>(&t);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = tf[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = __ldg(p + i);
-    }
+struct SmemLayout { int EP; size_t oImg, oE, oPart, oIdx, oXv, total; };
+__host__ __device__ inline SmemLayout smem_layout(int F, int K, int num) {
+    SmemLayout L;
+    const int C = F - num;
+    L.EP = e_pitch(F * K);
+    size_t o = 0;
+    L.oImg = o;  o += img_layout(F, K).total;
+    L.oE = o;    o += up16(sizeof(float) * kS * L.EP);
+    L.oPart = o; o += up16(sizeof(float) * K * kS);
+    L.oIdx = o;  o += up16(sizeof(int32_t) * kS * (C > 0 ? C : 1));
+    L.oXv = o;   o += up16(sizeof(float) * kS * (num > 0 ? num : 1));
+    L.total = o;
+    return L;
 }
 
-// Row segment [off, off+VEC) of field `fd` for category `idx` (already bounds-checked, < 2^31).
-template <int VEC>
-__device__ __forceinline__ void fetch_row(const dfw_field_desc& fd, int32_t idx, int K, int off, float (&v)[VEC]) {
-    uint32_t row = (uint32_t)idx, rem = 0;
-    if (fd.qr_op != DFW_TABLE_PLAIN) {          // model/QREmbeddingBag.py:157-158
-        const uint32_t c = (uint32_t)fd.collisions;
-        row = (uint32_t)idx / c;
-        rem = (uint32_t)idx - row * c;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------ pack kernel
+struct PackParams {
+    const dfw_field_desc* fields; const float* wl; const float* fm1; const float* cov;
+    unsigned char* image; int F, K; unsigned flags;
+};
+
+__global__ void __launch_bounds__(256) pack_shallow_kernel(const PackParams p) {
+    const int F = p.F, K = p.K, tid = threadIdx.x, lane = tid & 31;
+    const ImgLayout L = img_layout(F, K);
+    ImgHeader* hdr = reinterpret_cast<ImgHeader*>(p.image + L.oHdr);
+    float* U = reinterpret_cast<float*>(p.image + L.oU);
+    PairEnt* pairs = reinterpret_cast<PairEnt*>(p.image + L.oPairs);
+    float* wl = reinterpret_cast<float*>(p.image + L.oWl);
+    uint64_t* fd = reinterpret_cast<uint64_t*>(p.image + L.oFields);
+    const bool fwfm = p.flags & DFW_USE_FWFM;
+    __shared__ int s_live, s_qr, s_mis;
+    if (tid == 0) { s_live = 0; s_qr = 0; s_mis = 0; }
+    __syncthreads();
+    // field descriptors verbatim
+    for (int i = tid; i < F * (int)(sizeof(dfw_field_desc) / 8); i += blockDim.x)
+        fd[i] = reinterpret_cast<const uint64_t*>(p.fields)[i];
+    if (tid < F) {
+        const dfw_field_desc d = p.fields[tid];
+        if (d.qr_op != DFW_TABLE_PLAIN) s_qr = 1;
+        bool mis = (reinterpret_cast<uintptr_t>(d.w2) & 7) != 0;
+        for (int r = 0; r < d.n_ranks && r < DFW_MAX_RANKS; ++r) mis |= (reinterpret_cast<uintptr_t>(d.w2_shard[r]) & 7) != 0;
+        if (mis) s_mis = 1;
     }
+    // fwlw weights with the use_lw projection folded in: first = sum_f fm_1st[f] <E_f, wl_f>  (model/DeepFMs.py:344-345, 450)
+    for (int i = tid; i < F * K; i += blockDim.x) {
+        float w = 0.f;
+        if (p.flags & DFW_USE_FWLW) w = p.wl[i] * ((p.flags & DFW_USE_LW) ? p.fm1[i / K] : 1.0f);
+        wl[i] = w;
+    }
+    // U by columns, zero padded; (W.t() + W) * 0.5 in fp32 as the reference does (model/DeepFMs.py:364)
+    int live = 0;
+    for (int j = 1; j < F; ++j) {
+        for (int i = tid; i < pad4(j); i += blockDim.x) {
+            float u = 0.f;
+            if (i < j) u = fwfm ? (p.cov[j * F + i] + p.cov[i * F + j]) * 0.5f : 1.0f;
+            U[ucol_off(j) + i] = u;
+            live += (u != 0.f);
+        }
+    }
+    if (tid < 4) U[usize(F) + tid] = 0.f;
+    if (live) atomicAdd(&s_live, live);
+    // ordered compaction of the live pairs by one warp -> deterministic summation order
+    if (tid < 32) {
+        int n = 0;
+        for (int i = 0; i < F - 1; ++i) {
+            for (int jb = i + 1; jb < F; jb += 32) {
+                const int j = jb + lane;
+                float u = 0.f;
+                if (j < F) u = fwfm ? (p.cov[j * F + i] + p.cov[i * F + j]) * 0.5f : 1.0f;
+                const unsigned m = __ballot_sync(0xffffffffu, u != 0.f);
+                if (u != 0.f) {
+                    const int pos = n + __popc(m & ((1u << lane) - 1u));
+                    pairs[pos].ij = (uint32_t)(i * K) | ((uint32_t)(j * K) << 16);
+                    pairs[pos].u = u;
+                }
+                n += __popc(m);
+            }
+        }
+        if (lane == 0) hdr->n_list = n;
+    }
+    __syncthreads();
+    if (tid == 0) { hdr->live = s_live; hdr->any_qr = s_qr; hdr->misaligned = s_mis; }
+}
+
+// ------------------------------------------------------------------------------------------ gather helpers
+// Where the stored row of category `idx` of a field lives: quotient-remainder split
+// (model/QREmbeddingBag.py:157-158) and rank sharding (owner = row mod P, local row = row div P).
+__device__ __forceinline__ const float* locate_row(const dfw_field_desc& fd, int32_t idx, int K) {
+    uint32_t row = (uint32_t)idx;
+    if (fd.qr_op != DFW_TABLE_PLAIN) row = (uint32_t)idx / (uint32_t)fd.collisions;
     const float* base = fd.w2;
-    if (fd.n_ranks > 1) {                       // row-sharded: owner = row mod P, local row = row div P
+    if (fd.n_ranks > 1) {
         const uint32_t P = (uint32_t)fd.n_ranks;
         const uint32_t local = row / P;
         base = fd.w2_shard[row - local * P];
         row = local;
     }
-    ld_vec<VEC>(base + (int64_t)row * K + off, v);
-    if (fd.qr_op != DFW_TABLE_PLAIN) {
-        float r[VEC];
-        ld_vec<VEC>(fd.w2_r + rem * K + off, r);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = (fd.qr_op == DFW_TABLE_QR_MULT) ? v[i] * r[i] : v[i] + r[i];
+    return base + (int64_t)row * K;
+}
+
+// (q, r) = divmod(start + n * stride, d) advanced without divisions
+struct DivStep {
+    uint32_t q, r, dq, dr, d;
+    __device__ __forceinline__ DivStep(uint32_t start, uint32_t stride, uint32_t d_) : d(d_) {
+        q = start / d; r = start - q * d; dq = stride / d; dr = stride - dq * d;
+    }
+    __device__ __forceinline__ void next() { q += dq; r += dr; if (r >= d) { r -= d; ++q; } }
+};
+
+struct GatherCtx {
+    const dfw_field_desc* sF; const int32_t* sIdx; const float* sXv; float* sE;
+    int F, K, num, C, EP, nrows, tid, nthreads;
+};
+
+template <int SEGW, int FT, int KT>
+__device__ __forceinline__ void issue_rows(const GatherCtx& g) {
+    const uint32_t nV = (uint32_t)((KT > 0 ? KT : g.K) / SEGW);
+    const uint32_t per_sample = (uint32_t)(FT > 0 ? FT : g.F) * nV;
+    const uint32_t total = (uint32_t)g.nrows * per_sample;
+#pragma unroll 2
+    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
+        const uint32_t s = e / per_sample, r = e - s * per_sample;
+        const uint32_t f = r / nV, k = (r - f * nV) * SEGW;
+        const int32_t idx = (int)f < g.num ? 0 : g.sIdx[s * g.C + (f - g.num)];
+        const float* src = locate_row(g.sF[f], idx, g.K) + k;
+        float* dst = g.sE + s * g.EP + f * g.K + k;
+        if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
     }
 }
 
-__device__ __forceinline__ float fetch_first(const dfw_field_desc& fd, int32_t idx) {
-    if (fd.qr1_op != DFW_TABLE_PLAIN) {
-        const uint32_t c = (uint32_t)fd.collisions;
-        const uint32_t q = (uint32_t)idx / c, r = (uint32_t)idx - q * c;
-        const float a = __ldg(fd.w1 + q), b = __ldg(fd.w1_r + r);
-        return fd.qr1_op == DFW_TABLE_QR_MULT ? a * b : a + b;
+// quotient (*|+) remainder row for QR tables (model/QREmbeddingBag.py:169-172), times Xv for numeric fields
+// (model/DeepFMs.py:334): one fp32 operation each, applied by the thread that issued the copy.
+template <int SEGW, int FT, int KT>
+__device__ __forceinline__ void fixup_rows(const GatherCtx& g, bool any_qr) {
+    const uint32_t nV = (uint32_t)((KT > 0 ? KT : g.K) / SEGW);
+    const uint32_t per_sample = (uint32_t)(FT > 0 ? FT : g.F) * nV;
+    const uint32_t total = (uint32_t)g.nrows * per_sample;
+#pragma unroll 1
+    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
+        const uint32_t s = e / per_sample, r = e - s * per_sample;
+        const uint32_t f = r / nV, k = (r - f * nV) * SEGW;
+        const bool numeric = (int)f < g.num;
+        if (!any_qr && !numeric) continue;
+        const dfw_field_desc& fd = g.sF[f];
+        const bool qr = fd.qr_op != DFW_TABLE_PLAIN;
+        if (!qr && !numeric) continue;
+        float* dst = g.sE + s * g.EP + f * g.K + k;
+        float v0 = dst[0], v1 = SEGW == 2 ? dst[1] : 0.f;
+        if (qr) {
+            const int32_t idx = numeric ? 0 : g.sIdx[s * g.C + (f - g.num)];
+            const uint32_t c = (uint32_t)fd.collisions;
+            const uint32_t rem = (uint32_t)idx - ((uint32_t)idx / c) * c;
+            const float* rrow = fd.w2_r + rem * g.K + k;
+            const float r0 = __ldg(rrow), r1 = SEGW == 2 ? __ldg(rrow + 1) : 0.f;
+            if (fd.qr_op == DFW_TABLE_QR_MULT) { v0 *= r0; v1 *= r1; } else { v0 += r0; v1 += r1; }
+        }
+        if (numeric) { const float x = g.sXv[s * g.num + f]; v0 *= x; v1 *= x; }
+        dst[0] = v0;
+        if (SEGW == 2) dst[1] = v1;
     }
-    return __ldg(fd.w1 + idx);
 }
 
-template <int FT, int KT, int VEC>
-__global__ void __launch_bounds__(FT > 0 ? kSamples * KT : 1024)
+// ------------------------------------------------------------------------------------------ main kernel
+// FT/KT > 0: compile-time field count / embedding width (dense unrolled second order available).
+template <int FT, int KT>
+__global__ void __launch_bounds__(FT > 0 ? ((kS * KT + 31) / 32) * 32 : 512)
 embed_fwfm_kernel(const EmbedParams p) {
     const int F = FT > 0 ? FT : p.F;
     const int K = KT > 0 ? KT : p.K;
     const int num = p.num;
     const int C = F - num;
     const int FK = F * K;
-    const int lane = threadIdx.x;            // sample within the CTA
-    const int kk = threadIdx.y;              // embedding column owned in phase D
-    const int nthreads = kSamples * K;
-    const int tid = kk * kSamples + lane;
-    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int smp = tid & (kS - 1);          // sample within the CTA (phase D)
+    const int kk = tid >> 4;                 // embedding column owned in phase D (valid if < K)
+    const int64_t b0 = (int64_t)blockIdx.x * kS;
+    const int nrows = (int)min((int64_t)kS, p.B - b0);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = smem_layout(F, K, C);
-    float* sU = reinterpret_cast<float*>(smem_raw + L.oU);
-    PairEnt* sPairs = reinterpret_cast<PairEnt*>(smem_raw + L.oPairs);
-    dfw_field_desc* sF = reinterpret_cast<dfw_field_desc*>(smem_raw + L.oFields);
+    const SmemLayout L = smem_layout(F, K, num);
+    const ImgLayout IL = img_layout(F, K);
+    unsigned char* sImg = smem_raw + L.oImg;
+    const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg + IL.oHdr);
+    const float* sU = reinterpret_cast<const float*>(sImg + IL.oU);
+    const PairEnt* sPairs = reinterpret_cast<const PairEnt*>(sImg + IL.oPairs);
+    const float* sWl = reinterpret_cast<const float*>(sImg + IL.oWl);
+    const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + IL.oFields);
     float* sE = reinterpret_cast<float*>(smem_raw + L.oE);
-    float* sWl = reinterpret_cast<float*>(smem_raw + L.oWl);
     float* sPart = reinterpret_cast<float*>(smem_raw + L.oPart);
     int32_t* sIdx = reinterpret_cast<int32_t*>(smem_raw + L.oIdx);
-    int* sMisc = reinterpret_cast<int*>(smem_raw + L.oMisc);   // [0] = number of live pairs
+    float* sXv = reinterpret_cast<float*>(smem_raw + L.oXv);
     const int EP = L.EP;
-    const bool fwfm = p.flags & DFW_USE_FWFM;
     const bool fwlw = p.flags & DFW_USE_FWLW;
 
     // ------------------------------------------------------------------ phase A
-    {   // field descriptors (F x 120 B), copied as 8-byte words
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(p.fields);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(sF);
-        const int nw = F * (int)(sizeof(dfw_field_desc) / 8);
-        for (int i = tid; i < nw; i += nthreads) dst[i] = __ldg(src + i);
+    // batch inputs first: they come from DRAM; the shallow image is L2-resident model state
+    constexpr int kMaxIdx = 4, kMaxXv = 2;
+    int64_t myidx[kMaxIdx];
+    int mycol[kMaxIdx];
+    float myxv[kMaxXv];
+    const int nIdx = kS * C, nXv = kS * num;
+    {
+        DivStep st(tid, nthreads, C > 0 ? C : 1);
+#pragma unroll
+        for (int r = 0; r < kMaxIdx; ++r) {
+            myidx[r] = 0; mycol[r] = (int)st.r;
+            if (tid + r * nthreads < nIdx && (int)st.q < nrows) myidx[r] = p.xi[(b0 + st.q) * p.xi_sb + st.r * p.xi_sc];
+            st.next();
+        }
+        DivStep sv(tid, nthreads, num > 0 ? num : 1);
+#pragma unroll
+        for (int r = 0; r < kMaxXv; ++r) {
+            myxv[r] = 0.f;
+            if (tid + r * nthreads < nXv && (int)sv.q < nrows) myxv[r] = p.xv[(b0 + sv.q) * p.xv_sb + sv.r * p.xv_sc];
+            sv.next();
+        }
     }
-    if (fwlw) {   // fwlw weights; with use_lw the per-field projection fm_1st[f] is folded in (model/DeepFMs.py:450)
-        const bool lw = p.flags & DFW_USE_LW;
-        for (int i = tid; i < FK; i += nthreads) sWl[i] = __ldg(p.wl + i) * (lw ? __ldg(p.fm1 + i / K) : 1.0f);
-    }
-    if (tid == 0) sMisc[0] = 0;
-    __syncthreads();   // descriptors visible (rows needed for the bounds check)
+#pragma unroll 2
+    for (uint32_t i = tid; i < (uint32_t)(IL.total >> 4); i += nthreads) cp_async16(sImg + 16 * i, p.image + 16 * i);
+    cp_async_wait_all();
+    __syncthreads();   // image visible (row counts for the bounds check)
 
-    for (int e = tid; e < kSamples * C; e += nthreads) {
-        const int s = e / C, c = e - s * C;
-        const int64_t b = b0 + s;
-        int64_t idx = 0;
-        if (b < p.B) {
-            idx = p.xi[b * p.xi_sb + c * p.xi_sc];
+#pragma unroll
+    for (int r = 0; r < kMaxIdx; ++r) {
+        const int e = tid + r * nthreads;
+        if (e < nIdx) {
+            const int c = mycol[r];
+            int64_t idx = myidx[r];
             if (idx < 0 || idx >= sF[num + c].rows) {   // defined behaviour instead of a wild read
                 if (p.err) atomicExch(p.err, 1 + num + c);
                 idx = 0;
             }
+            sIdx[e] = (int32_t)idx;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxXv; ++r) {
+        const int e = tid + r * nthreads;
+        if (e < nXv) sXv[e] = myxv[r];
+    }
+#pragma unroll 1
+    for (uint32_t e = tid + kMaxXv * nthreads; e < (uint32_t)nXv; e += nthreads) {      // small CTAs only
+        const uint32_t s = e / (uint32_t)num, f = e - s * num;
+        sXv[e] = (int)s < nrows ? p.xv[(b0 + s) * p.xv_sb + f * p.xv_sc] : 0.f;
+    }
+#pragma unroll 1
+    for (uint32_t e = tid + kMaxIdx * nthreads; e < (uint32_t)nIdx; e += nthreads) {    // small CTAs only
+        const uint32_t s = e / (uint32_t)C, c = e - s * C;
+        int64_t idx = (int)s < nrows ? p.xi[(b0 + s) * p.xi_sb + c * p.xi_sc] : 0;
+        if (idx < 0 || idx >= sF[num + c].rows) {
+            if (p.err) atomicExch(p.err, 1 + num + c);
+            idx = 0;
         }
         sIdx[e] = (int32_t)idx;
     }
-
-    // U = upper triangle of (W + W^T)/2 (model/DeepFMs.py:364), rows padded to float4; FM: ones.
-    // Warp w builds rows w, w+nwarps, ...; the live-pair count decides dense vs pair-list walking.
-    if constexpr (FT > 0) {
-        const int nwarps = K;
-        int live = 0;
-        for (int i = kk; i < F - 1; i += nwarps) {
-            const int off = urow_off(F, i);
-            const int width = pad4(F - 1 - i);
-            for (int jj = lane; jj < width; jj += 32) {
-                const int j = i + 1 + jj;
-                float u = 0.f;
-                if (j < F) u = fwfm ? (__ldg(p.cov + j * F + i) + __ldg(p.cov + i * F + j)) * 0.5f : 1.0f;
-                sU[off + jj] = u;
-                live += (u != 0.f);
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
-        if (lane == 0 && live) atomicAdd(&sMisc[0], live);
-    }
-    __syncthreads();   // indices + U + live count visible
+    __syncthreads();   // indices + dense values visible
 
     const int P = F * (F - 1) / 2;
-    const bool use_list = (FT == 0) || (sMisc[0] * 6 < P);
-    if (use_list && kk == 0) {
-        // ordered compaction of the live pairs by one warp -> deterministic summation order
-        int n = 0;
-        for (int i = 0; i < F - 1; ++i) {
-            for (int jb = i + 1; jb < F; jb += 32) {
-                const int j = jb + lane;
-                float u = 0.f;
-                if (j < F) u = fwfm ? (__ldg(p.cov + j * F + i) + __ldg(p.cov + i * F + j)) * 0.5f : 1.0f;
-                const unsigned m = __ballot_sync(0xffffffffu, u != 0.f);
-                if (u != 0.f) {
-                    const int pos = n + __popc(m & ((1u << lane) - 1u));
-                    sPairs[pos].ij = (uint32_t)(i * K) | ((uint32_t)(j * K) << 16);
-                    sPairs[pos].u = u;
-                }
-                n += __popc(m);
-            }
-        }
-        if (lane == 0) sMisc[1] = n;
+    const bool use_list = (FT == 0) || (hdr->live * 6 < P);
+    const bool any_qr = hdr->any_qr != 0;
+    const bool vec2 = hdr->misaligned == 0 && (K % 2 == 0);    // all row bases 8-byte aligned
+
+    // ------------------------------------------------------------------ phase B: gather
+    GatherCtx g{sF, sIdx, sXv, sE, F, K, num, C, EP, nrows, tid, nthreads};
+    if (vec2) issue_rows<2, FT, KT>(g); else issue_rows<1, FT, KT>(g);
+    // rows of samples past the end of the batch: zeros (never written out, keeps phase D finite)
+#pragma unroll 1
+    for (uint32_t e = tid; e < (uint32_t)((kS - nrows) * FK); e += nthreads) {
+        const uint32_t s = e / (uint32_t)FK;
+        sE[(nrows + s) * EP + (e - s * FK)] = 0.f;
     }
 
-    // first-order table values of this thread's fields f = kk, kk+K, ... (requested early, used in phase D)
+    // first-order table values of this thread's fields f = kk, kk+K, ...   (model/DeepFMs.py:300-309)
     float first_acc = 0.f;
-    const int64_t bme = b0 + lane;
-    const bool live_sample = bme < p.B;
-    if (!fwlw && live_sample) {
+    const bool owner = kk < K;
+    const bool live_sample = smp < nrows;
+    if (!fwlw && live_sample && owner) {
+#pragma unroll 4
         for (int f = kk; f < F; f += K) {
+            const dfw_field_desc& fd = sF[f];
+            const int32_t idx = f < num ? 0 : sIdx[smp * C + (f - num)];
             float v;
-            if (f < num) v = fetch_first(sF[f], 0) * p.xv[bme * p.xv_sb + f * p.xv_sc];   // model/DeepFMs.py:302-304
-            else v = fetch_first(sF[f], sIdx[lane * C + (f - num)]);
+            if (fd.qr1_op != DFW_TABLE_PLAIN) {
+                const uint32_t c = (uint32_t)fd.collisions;
+                const uint32_t q = (uint32_t)idx / c, r = (uint32_t)idx - q * c;
+                const float a = __ldg(fd.w1 + q), b = __ldg(fd.w1_r + r);
+                v = fd.qr1_op == DFW_TABLE_QR_MULT ? a * b : a + b;
+            } else {
+                v = __ldg(fd.w1 + idx);
+            }
+            if (f < num) v *= sXv[smp * num + f];
             if (p.flags & DFW_USE_LW) v *= __ldg(p.fm1 + f);                              // model/DeepFMs.py:450
             first_acc += v;
         }
     }
 
-    // ------------------------------------------------------------------ phase B: gather
-    {
-        const int nV = K / VEC;
-        const int per_sample = F * nV;
-        const int total = kSamples * per_sample;
-        if constexpr (FT > 0) {
-            constexpr int FTc = FT > 0 ? FT : 1, KTc = KT > 0 ? KT : 1;
-            constexpr int TOTAL = kSamples * FTc * (KTc / VEC);
-            constexpr int NT = kSamples * KTc;
-            constexpr int ITEMS = (TOTAL + NT - 1) / NT;
-            float v[ITEMS][VEC];
-#pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int e = tid + it * NT;
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) v[it][i] = 0.f;
-                if (e < TOTAL) {
-                    const int s = e / per_sample, r = e - s * per_sample;
-                    const int f = r / nV, off = (r - f * nV) * VEC;
-                    const int64_t b = b0 + s;
-                    if (b < p.B) {
-                        if (f < num) {
-                            fetch_row<VEC>(sF[f], 0, K, off, v[it]);
-                            const float x = p.xv[b * p.xv_sb + f * p.xv_sc];
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) v[it][i] *= x;               // model/DeepFMs.py:334
-                        } else {
-                            fetch_row<VEC>(sF[f], sIdx[s * C + (f - num)], K, off, v[it]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < ITEMS; ++it) {
-                const int e = tid + it * NT;
-                if (e < TOTAL) {
-                    const int s = e / per_sample, r = e - s * per_sample;
-                    const int f = r / nV, off = (r - f * nV) * VEC;
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) sE[s * EP + f * K + off + i] = v[it][i];
-                }
-            }
-        } else {
-            for (int e0 = tid; e0 < total; e0 += 4 * nthreads) {
-                float v[4][VEC];
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int e = e0 + it * nthreads;
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) v[it][i] = 0.f;
-                    if (e < total) {
-                        const int s = e / per_sample, r = e - s * per_sample;
-                        const int f = r / nV, off = (r - f * nV) * VEC;
-                        const int64_t b = b0 + s;
-                        if (b < p.B) {
-                            if (f < num) {
-                                fetch_row<VEC>(sF[f], 0, K, off, v[it]);
-                                const float x = p.xv[b * p.xv_sb + f * p.xv_sc];
-#pragma unroll
-                                for (int i = 0; i < VEC; ++i) v[it][i] *= x;
-                            } else {
-                                fetch_row<VEC>(sF[f], sIdx[s * C + (f - num)], K, off, v[it]);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int e = e0 + it * nthreads;
-                    if (e < total) {
-                        const int s = e / per_sample, r = e - s * per_sample;
-                        const int f = r / nV, off = (r - f * nV) * VEC;
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) sE[s * EP + f * K + off + i] = v[it][i];
-                    }
-                }
-            }
-        }
+    cp_async_wait_all();   // this thread's segments have landed: fix them up in place
+    if (any_qr || num > 0) {
+        if (vec2) fixup_rows<2, FT, KT>(g, any_qr); else fixup_rows<1, FT, KT>(g, any_qr);
     }
-    __syncthreads();   // E block + pair list complete
+    __syncthreads();   // E block complete
 
     // ------------------------------------------------------------------ phase C: stream E out
-    const int nrows = (int)min((int64_t)kSamples, p.B - b0);
     if (p.E) {
         const int ld = (int)p.ldE;
         float* dst = p.E + b0 * p.ldE;
-        int s = tid / ld, c = tid - s * ld;                      // (row, column) advanced without divisions
-        const int ds = nthreads / ld, dc = nthreads - ds * ld;
+        DivStep st(tid, nthreads, ld);
+#pragma unroll 2
         for (int i = tid; i < nrows * ld; i += nthreads) {
-            dst[i] = c < FK ? sE[s * EP + c] : 0.f;
-            s += ds; c += dc;
-            if (c >= ld) { c -= ld; ++s; }
+            dst[i] = (int)st.r < FK ? sE[st.q * EP + st.r] : 0.f;
+            st.next();
         }
     }
     if (p.Eb) {
         const int ld2 = (int)(p.ldEb >> 1);
         __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(p.Eb + b0 * p.ldEb);
-        int s = tid / ld2, c = tid - s * ld2;
-        const int ds = nthreads / ld2, dc = nthreads - ds * ld2;
+        DivStep st(tid, nthreads, ld2);
+#pragma unroll 2
         for (int i = tid; i < nrows * ld2; i += nthreads) {
-            const int c0 = 2 * c;
-            const float lo = c0 < FK ? sE[s * EP + c0] : 0.f;
-            const float hi = c0 + 1 < FK ? sE[s * EP + c0 + 1] : 0.f;
+            const int c0 = 2 * (int)st.r;
+            const float lo = c0 < FK ? sE[st.q * EP + c0] : 0.f;
+            const float hi = c0 + 1 < FK ? sE[st.q * EP + c0 + 1] : 0.f;
             dst[i] = __floats2bfloat162_rn(lo, hi);
-            s += ds; c += dc;
-            if (c >= ld2) { c -= ld2; ++s; }
+            st.next();
         }
     }
 
     // ------------------------------------------------------------------ phase D: first + second order
-    const float* myE = sE + lane * EP + kk;   // E[s][f][k] at myE[f*K]
-    float acc = first_acc;
-    if (fwlw) {                                // model/DeepFMs.py:344-345
-        float a1 = 0.f;
-        for (int f = 0; f < F; ++f) a1 = fmaf(myE[f * K], sWl[f * K + kk], a1);
-        acc = a1;
-    }
-    float second = 0.f;
-    if (use_list) {
-        const int n = sMisc[1];
-        float s0 = 0.f, s1 = 0.f;
-        int q = 0;
-        for (; q + 1 < n; q += 2) {
-            const PairEnt a = sPairs[q], b = sPairs[q + 1];
-            s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
-            s1 = fmaf(b.u * myE[b.ij & 0xffffu], myE[b.ij >> 16], s1);
-        }
-        if (q < n) {
-            const PairEnt a = sPairs[q];
-            s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
-        }
-        second = s0 + s1;
-    } else if constexpr (FT > 0) {
-        constexpr int FTc = FT > 0 ? FT : 2, KTc = KT > 0 ? KT : 1;
-        float e[FTc];
-#pragma unroll
-        for (int f = 0; f < FTc; ++f) e[f] = myE[f * KTc];
-        const float4* sU4 = reinterpret_cast<const float4*>(sU);
-#pragma unroll
-        for (int i = 0; i < FTc - 1; ++i) {
-            const int off4 = urow_off(FTc, i) >> 2;
-            float t = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < pad4(FTc - 1 - i) / 4; ++c4) {
-                const float4 u = sU4[off4 + c4];
-                const int j = i + 1 + 4 * c4;
-                if (j + 0 < FTc) t = fmaf(u.x, e[j + 0 < FTc ? j + 0 : 0], t);
-                if (j + 1 < FTc) t = fmaf(u.y, e[j + 1 < FTc ? j + 1 : 0], t);
-                if (j + 2 < FTc) t = fmaf(u.z, e[j + 2 < FTc ? j + 2 : 0], t);
-                if (j + 3 < FTc) t = fmaf(u.w, e[j + 3 < FTc ? j + 3 : 0], t);
+    if (owner) {
+        const float* myE = sE + smp * EP + kk;   // E[s][f][k] at myE[f*K]
+        float acc = first_acc;
+        if (fwlw) {                                // model/DeepFMs.py:344-345
+            float a0 = 0.f, a1 = 0.f;
+            int f = 0;
+#pragma unroll 2
+            for (; f + 1 < F; f += 2) {
+                a0 = fmaf(myE[f * K], sWl[f * K + kk], a0);
+                a1 = fmaf(myE[(f + 1) * K], sWl[(f + 1) * K + kk], a1);
             }
-            second = fmaf(e[i], t, second);
+            if (f < F) a0 = fmaf(myE[f * K], sWl[f * K + kk], a0);
+            acc = a0 + a1;
         }
+        float second = 0.f;
+        if (use_list) {
+            const int n = hdr->n_list;
+            float s0 = 0.f, s1 = 0.f;
+            int q = 0;
+#pragma unroll 1
+            for (; q + 1 < n; q += 2) {
+                const PairEnt a = sPairs[q], b = sPairs[q + 1];
+                s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
+                s1 = fmaf(b.u * myE[b.ij & 0xffffu], myE[b.ij >> 16], s1);
+            }
+            if (q < n) {
+                const PairEnt a = sPairs[q];
+                s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
+            }
+            second = s0 + s1;
+        } else if constexpr (FT > 0) {
+            constexpr int FTc = FT > 0 ? FT : 2, KTc = KT > 0 ? KT : 1;
+            float e[FTc], t[FTc];
+#pragma unroll
+            for (int f = 0; f < FTc; ++f) { e[f] = myE[f * KTc]; t[f] = 0.f; }
+            const float4* sU4 = reinterpret_cast<const float4*>(sU);
+#pragma unroll
+            for (int j = 1; j < FTc; ++j) {
+                const int off4 = ucol_off(j) >> 2;
+#pragma unroll
+                for (int c4 = 0; c4 < pad4(j) / 4; ++c4) {
+                    const float4 u = sU4[off4 + c4];
+                    const int i = 4 * c4;
+                    if (i + 0 < j) t[i + 0] = fmaf(u.x, e[j], t[i + 0]);
+                    if (i + 1 < j) t[i + 1 < FTc ? i + 1 : 0] = fmaf(u.y, e[j], t[i + 1 < FTc ? i + 1 : 0]);
+                    if (i + 2 < j) t[i + 2 < FTc ? i + 2 : 0] = fmaf(u.z, e[j], t[i + 2 < FTc ? i + 2 : 0]);
+                    if (i + 3 < j) t[i + 3 < FTc ? i + 3 : 0] = fmaf(u.w, e[j], t[i + 3 < FTc ? i + 3 : 0]);
+                }
+            }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i + 1 < FTc; i += 2) {
+                s0 = fmaf(e[i], t[i], s0);
+                if (i + 1 < FTc - 1) s1 = fmaf(e[i + 1], t[i + 1], s1);
+            }
+            second = s0 + s1;
+        }
+        sPart[kk * kS + smp] = acc + second;
     }
-    sPart[kk * kSamples + lane] = acc + second;
     __syncthreads();
 
     // ------------------------------------------------------------------ phase E: reduce over k
-    if (kk == 0 && live_sample) {
+    if (tid < nrows) {
         float tot = 0.f;
-        for (int k = 0; k < K; ++k) tot += sPart[k * kSamples + lane];
-        p.shallow[bme] = tot + __ldg(p.bias);
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) tot += sPart[k * kS + tid];
+        p.shallow[b0 + tid] = tot + __ldg(p.bias);
     }
 }
 
-template <int FT, int KT, int VEC>
+template <int FT, int KT>
 static int launch_embed(const EmbedParams& p, cudaStream_t st) {
-    const int F = p.F, K = p.K, C = F - p.num;
-    const SmemLayout L = smem_layout(F, K, C);
-    auto kern = embed_fwfm_kernel<FT, KT, VEC>;
-    static thread_local size_t configured = 0;
-    if (L.total > 48 * 1024 && L.total > configured) {
+    const SmemLayout L = smem_layout(p.F, p.K, p.num);
+    auto kern = embed_fwfm_kernel<FT, KT>;
+    DFW_REQUIRE(L.total <= 227 * 1024, DFW_E_UNSUPPORTED, "embed kernel needs %zu B of shared memory", L.total);
+    if (L.total > 48 * 1024)
         DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        configured = L.total;
-    }
-    const dim3 block(kSamples, K);
-    const dim3 grid((unsigned)((p.B + kSamples - 1) / kSamples));
-    kern<<<grid, block, L.total, st>>>(p);
+    const int threads = ((kS * p.K + 31) / 32) * 32;
+    const unsigned grid = (unsigned)((p.B + kS - 1) / kS);
+    kern<<<grid, threads, L.total, st>>>(p);
     count_launch();
     return check_launch("embed_fwfm_kernel");
 }
 
 }  // namespace dfw
 
+extern "C" size_t dfw_shallow_image_bytes(const dfw_model* m) {
+    if (!m || m->field_size < 1 || m->embedding_size < 1) return 0;
+    return dfw::img_layout(m->field_size, m->embedding_size).total;
+}
+
+extern "C" int dfw_pack_shallow(const dfw_model* m, void* image, void* stream) {
+    using namespace dfw;
+    if (int rc = check_model(m)) return rc;
+    DFW_REQUIRE(image && (reinterpret_cast<uintptr_t>(image) & 15) == 0, DFW_E_ARG, "image must be 16-byte aligned");
+    DFW_REQUIRE((int64_t)m->field_size * m->embedding_size < 65536, DFW_E_UNSUPPORTED, "F*K must be < 65536");
+    PackParams p{m->fields, m->fwfm_linear, m->fm_1st, m->field_cov, static_cast<unsigned char*>(image),
+                 m->field_size, m->embedding_size, m->flags};
+    pack_shallow_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    count_launch();
+    return check_launch("pack_shallow_kernel");
+}
+
 extern "C" int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
                               const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B,
                               float* E_out, int64_t ldE, void* E_bf16_out, int64_t ldEb,
-                              float* shallow_out, int32_t* err_word, int32_t my_rank, void* stream) {
+                              float* shallow_out, int32_t* err_word, void* stream) {
     using namespace dfw;
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");
     if (B == 0) return 0;
     const int F = m->field_size, K = m->embedding_size, num = m->numerical;
+    DFW_REQUIRE(m->shallow_image, DFW_E_ARG, "model has no shallow image (call dfw_pack_shallow)");
     DFW_REQUIRE(shallow_out, DFW_E_ARG, "shallow_out is NULL");
     DFW_REQUIRE(F - num == 0 || xi, DFW_E_ARG, "xi is NULL");
     DFW_REQUIRE(num == 0 || xv, DFW_E_ARG, "xv is NULL");
     DFW_REQUIRE(!E_out || ldE >= (int64_t)F * K, DFW_E_ARG, "ldE %lld < F*K", (long long)ldE);
     DFW_REQUIRE(!E_bf16_out || (ldEb >= (int64_t)F * K && ldEb % 2 == 0), DFW_E_ARG, "ldEb must be even and >= F*K");
-    DFW_REQUIRE((int64_t)F * K < 65536, DFW_E_UNSUPPORTED, "F*K must be < 65536");
     EmbedParams p;
-    p.fields = m->fields;
+    p.image = static_cast<const unsigned char*>(m->shallow_image);
     p.xi = xi; p.xi_sb = xi_stride_b; p.xi_sc = xi_stride_c;
     p.xv = xv; p.xv_sb = xv_stride_b; p.xv_sc = xv_stride_c;
-    p.wl = m->fwfm_linear; p.fm1 = m->fm_1st; p.cov = m->field_cov; p.bias = m->bias;
+    p.fm1 = m->fm_1st; p.bias = m->bias;
     p.E = E_out; p.ldE = ldE; p.Eb = reinterpret_cast<__nv_bfloat16*>(E_bf16_out); p.ldEb = ldEb;
     p.shallow = shallow_out; p.err = (m->flags & DFW_CHECK_INDEX) ? err_word : nullptr;
-    p.B = B; p.F = F; p.num = num; p.K = K; p.flags = m->flags; p.my_rank = my_rank;
+    p.B = B; p.F = F; p.num = num; p.K = K; p.flags = m->flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    // the two dataset shapes BASELINE.json names get fully unrolled instantiations
-    if (F == 39 && K == 10) return launch_embed<39, 10, 2>(p, st);
-    if (F == 47 && K == 10) return launch_embed<47, 10, 2>(p, st);
-    if (K % 4 == 0) return launch_embed<0, 0, 4>(p, st);
-    if (K % 2 == 0) return launch_embed<0, 0, 2>(p, st);
-    return launch_embed<0, 0, 1>(p, st);
+    // the two dataset shapes BASELINE.json names get the fully unrolled dense second order
+    if (F == 39 && K == 10) return launch_embed<39, 10>(p, st);
+    if (F == 47 && K == 10) return launch_embed<47, 10>(p, st);
+    return launch_embed<0, 0>(p, st);
 }

@@ -21,11 +21,12 @@ purpose:
 * inference only: ``forward`` in ``train()`` mode with dropout, ``fit`` and the KD helpers raise;
 * ``logger=None`` is accepted.
 
-The kernels read the module's parameters in place (pointer table in device memory), so in-place
-weight edits are seen by the next call.  Derived images (bf16 MLP weights for the tcgen05 path, CSR
-for the pruned-MLP path) are rebuilt whenever the module is moved, re-loaded, re-initialised,
-switched with ``train()/eval()`` -- every reference inference entry point calls ``eval()`` first --
-or on ``repack()``.
+The kernels read the embedding tables and the fp32 MLP weights in place (pointer table in device
+memory), so in-place edits of those are seen by the next call.  Derived images -- the shallow image
+(symmetrised ``field_cov`` / pair list, ``fwfm_linear`` x ``fm_1st``, descriptors), bf16 MLP weights
+for the tcgen05 path, CSR for the pruned-MLP path -- are rebuilt whenever the module is moved,
+re-loaded, re-initialised, switched with ``train()/eval()`` (every reference inference entry point
+calls ``eval()`` first, model/DeepFMs.py:757, 859, 870) or on ``repack()``.
 """
 from __future__ import annotations
 
@@ -144,6 +145,13 @@ class _Plan:
         self.model_ref = C.byref(m)
         self.params = params
         self.ptrs = tuple(p.data_ptr() for p in params)
+        # shallow image: U / pair list / fwlw weights / descriptors in the kernel's shared-memory layout
+        nimg = lib.dfw_shallow_image_bytes(self.model_ref)
+        self.shallow_image = torch.zeros(nimg, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.dfw_pack_shallow(self.model_ref, self.shallow_image.data_ptr(), _stream_ptr(dev)),
+                       "dfw_pack_shallow")
+        m.shallow_image = self.shallow_image.data_ptr()
         self.images = set()     # which derived images exist: "bf16", "csr"
         self.workspace = None
         self.host_ws = None
@@ -483,7 +491,7 @@ class DeepFMs(nn.Module):
         with torch.cuda.device(dev):
             rc = _lib.load().dfw_embed_fwfm(plan.model_ref, Xi.data_ptr(), Xi.stride(0), Xi.stride(1),
                                             Xv.data_ptr() if self.num else None, Xv.stride(0), Xv.stride(1), B,
-                                            E.data_ptr(), FK, None, 0, shallow.data_ptr(), None, 0, _stream_ptr(dev))
+                                            E.data_ptr(), FK, None, 0, shallow.data_ptr(), None, _stream_ptr(dev))
         _lib.check(rc, "dfw_embed_fwfm")
         return E.view(B, self.field_size, self.embedding_size), shallow
 
@@ -641,8 +649,11 @@ def _single_table_lookup(table: QREmbeddingBag, idx: torch.Tensor) -> torch.Tens
     idx = idx.to(torch.int64)
     E = torch.empty(B, K, dtype=torch.float32, device=dev)
     shallow = torch.empty(max(B, 1), dtype=torch.float32, device=dev)
+    img = torch.zeros(lib.dfw_shallow_image_bytes(C.byref(m)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
+        _lib.check(lib.dfw_pack_shallow(C.byref(m), img.data_ptr(), _stream_ptr(dev)), "dfw_pack_shallow")
+        m.shallow_image = img.data_ptr()
         rc = lib.dfw_embed_fwfm(C.byref(m), idx.data_ptr(), idx.stride(0), 0, None, 0, 0, B, E.data_ptr(), K,
-                                None, 0, shallow.data_ptr(), None, 0, _stream_ptr(dev))
+                                None, 0, shallow.data_ptr(), None, _stream_ptr(dev))
     _lib.check(rc, "dfw_embed_fwfm")
     return E
