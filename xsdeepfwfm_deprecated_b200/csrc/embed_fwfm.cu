@@ -40,10 +40,11 @@ struct EmbedParams {
     const float* fm1; const float* bias;
     float* E; int64_t ldE; __nv_bfloat16* Eb; int64_t ldEb; float* shallow; int32_t* err;
     int64_t B; int F, num, K; unsigned flags;
+    long long* clk;   // optional per-CTA phase timestamps (debug tooling, see dfw_debug_set_clock_buffer)
 };
 
 struct PairEnt { uint32_t ij; float u; };  // ij = (i*K) | (j*K) << 16
-struct ImgHeader { int32_t live, n_list, any_qr, misaligned; };
+struct ImgHeader { int32_t live, n_list, any_special, misaligned; };   // any_special: some table is QR or rank-sharded
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 // column j of the strict upper triangle holds U_0j .. U_(j-1)j, padded to a multiple of 4 floats:
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256) pack_shallow_kernel(const PackParams p) {
         fd[i] = reinterpret_cast<const uint64_t*>(p.fields)[i];
     if (tid < F) {
         const dfw_field_desc d = p.fields[tid];
-        if (d.qr_op != DFW_TABLE_PLAIN) s_qr = 1;
+        if (d.qr_op != DFW_TABLE_PLAIN || d.n_ranks > 1) s_qr = 1;
         bool mis = (reinterpret_cast<uintptr_t>(d.w2) & 7) != 0;
         for (int r = 0; r < d.n_ranks && r < DFW_MAX_RANKS; ++r) mis |= (reinterpret_cast<uintptr_t>(d.w2_shard[r]) & 7) != 0;
         if (mis) s_mis = 1;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) pack_shallow_kernel(const PackParams p) {
         if (lane == 0) hdr->n_list = n;
     }
     __syncthreads();
-    if (tid == 0) { hdr->live = s_live; hdr->any_qr = s_qr; hdr->misaligned = s_mis; }
+    if (tid == 0) { hdr->live = s_live; hdr->any_special = s_qr; hdr->misaligned = s_mis; }
 }
 
 // ------------------------------------------------------------------------------------------ gather helpers
@@ -197,51 +198,58 @@ struct GatherCtx {
     int F, K, num, C, EP, nrows, tid, nthreads;
 };
 
-template <int SEGW, int FT, int KT>
+// Adjacent lanes take adjacent 8-byte (SEGW = 2: all row bases 8-byte aligned, K even) or 4-byte pieces of the
+// same row, so one warp instruction touches ~7 rows / cache lines instead of 32 (LSU wavefronts are the cost
+// of a gather); all pieces of the block are in flight together, global -> SMEM without register staging.
+// PLAIN = no table of the model is QR or rank-sharded: branch-free body (row = w2 + idx * K).
+template <int SEGW, int FT, int KT, bool PLAIN>
 __device__ __forceinline__ void issue_rows(const GatherCtx& g) {
-    const uint32_t nV = (uint32_t)((KT > 0 ? KT : g.K) / SEGW);
-    const uint32_t per_sample = (uint32_t)(FT > 0 ? FT : g.F) * nV;
-    const uint32_t total = (uint32_t)g.nrows * per_sample;
-#pragma unroll 2
+    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
+    const int K = KT > 0 ? KT : g.K;
+    const uint32_t nV = (uint32_t)(K / SEGW);
+    const uint32_t total = (uint32_t)g.nrows * F * nV;
+#pragma unroll 4
     for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t s = e / per_sample, r = e - s * per_sample;
-        const uint32_t f = r / nV, k = (r - f * nV) * SEGW;
+        const uint32_t row = e / nV, k = (e - row * nV) * SEGW;
+        const uint32_t s = row / F, f = row - s * F;
         const int32_t idx = (int)f < g.num ? 0 : g.sIdx[s * g.C + (f - g.num)];
-        const float* src = locate_row(g.sF[f], idx, g.K) + k;
-        float* dst = g.sE + s * g.EP + f * g.K + k;
+        const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
+        float* dst = g.sE + s * g.EP + f * K + k;
         if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
     }
 }
 
 // quotient (*|+) remainder row for QR tables (model/QREmbeddingBag.py:169-172), times Xv for numeric fields
-// (model/DeepFMs.py:334): one fp32 operation each, applied by the thread that issued the copy.
-template <int SEGW, int FT, int KT>
+// (model/DeepFMs.py:334): one fp32 operation each, applied after the block's copies have landed.
+template <int FT, int KT>
 __device__ __forceinline__ void fixup_rows(const GatherCtx& g, bool any_qr) {
-    const uint32_t nV = (uint32_t)((KT > 0 ? KT : g.K) / SEGW);
-    const uint32_t per_sample = (uint32_t)(FT > 0 ? FT : g.F) * nV;
-    const uint32_t total = (uint32_t)g.nrows * per_sample;
+    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
+    const int K = KT > 0 ? KT : g.K;
+    const uint32_t total = (uint32_t)g.nrows * F;
 #pragma unroll 1
     for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t s = e / per_sample, r = e - s * per_sample;
-        const uint32_t f = r / nV, k = (r - f * nV) * SEGW;
+        const uint32_t s = e / F, f = e - s * F;
         const bool numeric = (int)f < g.num;
         if (!any_qr && !numeric) continue;
         const dfw_field_desc& fd = g.sF[f];
-        const bool qr = fd.qr_op != DFW_TABLE_PLAIN;
-        if (!qr && !numeric) continue;
-        float* dst = g.sE + s * g.EP + f * g.K + k;
-        float v0 = dst[0], v1 = SEGW == 2 ? dst[1] : 0.f;
-        if (qr) {
+        const int op = fd.qr_op;
+        if (op == DFW_TABLE_PLAIN && !numeric) continue;
+        float* dst = g.sE + s * g.EP + f * K;
+        const float x = numeric ? g.sXv[s * g.num + f] : 1.0f;
+        const float* rrow = nullptr;
+        if (op != DFW_TABLE_PLAIN) {
             const int32_t idx = numeric ? 0 : g.sIdx[s * g.C + (f - g.num)];
             const uint32_t c = (uint32_t)fd.collisions;
-            const uint32_t rem = (uint32_t)idx - ((uint32_t)idx / c) * c;
-            const float* rrow = fd.w2_r + rem * g.K + k;
-            const float r0 = __ldg(rrow), r1 = SEGW == 2 ? __ldg(rrow + 1) : 0.f;
-            if (fd.qr_op == DFW_TABLE_QR_MULT) { v0 *= r0; v1 *= r1; } else { v0 += r0; v1 += r1; }
+            rrow = fd.w2_r + ((uint32_t)idx - ((uint32_t)idx / c) * c) * K;
         }
-        if (numeric) { const float x = g.sXv[s * g.num + f]; v0 *= x; v1 *= x; }
-        dst[0] = v0;
-        if (SEGW == 2) dst[1] = v1;
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            float v = dst[k];
+            if (op == DFW_TABLE_QR_MULT) v *= __ldg(rrow + k);
+            else if (op == DFW_TABLE_QR_ADD) v += __ldg(rrow + k);
+            if (numeric) v *= x;
+            dst[k] = v;
+        }
     }
 }
 
@@ -278,6 +286,9 @@ embed_fwfm_kernel(const EmbedParams p) {
     const int EP = L.EP;
     const bool fwlw = p.flags & DFW_USE_FWLW;
 
+#define DFW_CLK(slot) do { if (p.clk && tid == 0) p.clk[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
+    if (p.clk && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.clk[blockIdx.x * 8 + 7] = (long long)t; }
+    DFW_CLK(0);
     // ------------------------------------------------------------------ phase A
     // batch inputs first: they come from DRAM; the shallow image is L2-resident model state
     constexpr int kMaxIdx = 4, kMaxXv = 2;
@@ -305,6 +316,7 @@ embed_fwfm_kernel(const EmbedParams p) {
     for (uint32_t i = tid; i < (uint32_t)(IL.total >> 4); i += nthreads) cp_async16(sImg + 16 * i, p.image + 16 * i);
     cp_async_wait_all();
     __syncthreads();   // image visible (row counts for the bounds check)
+    DFW_CLK(1);
 
 #pragma unroll
     for (int r = 0; r < kMaxIdx; ++r) {
@@ -340,15 +352,17 @@ embed_fwfm_kernel(const EmbedParams p) {
         sIdx[e] = (int32_t)idx;
     }
     __syncthreads();   // indices + dense values visible
+    DFW_CLK(2);
 
     const int P = F * (F - 1) / 2;
     const bool use_list = (FT == 0) || (hdr->live * 6 < P);
-    const bool any_qr = hdr->any_qr != 0;
+    const bool any_qr = hdr->any_special != 0;
     const bool vec2 = hdr->misaligned == 0 && (K % 2 == 0);    // all row bases 8-byte aligned
 
     // ------------------------------------------------------------------ phase B: gather
     GatherCtx g{sF, sIdx, sXv, sE, F, K, num, C, EP, nrows, tid, nthreads};
-    if (vec2) issue_rows<2, FT, KT>(g); else issue_rows<1, FT, KT>(g);
+    if (!any_qr) { if (vec2) issue_rows<2, FT, KT, true>(g); else issue_rows<1, FT, KT, true>(g); }
+    else         { if (vec2) issue_rows<2, FT, KT, false>(g); else issue_rows<1, FT, KT, false>(g); }
     // rows of samples past the end of the batch: zeros (never written out, keeps phase D finite)
 #pragma unroll 1
     for (uint32_t e = tid; e < (uint32_t)((kS - nrows) * FK); e += nthreads) {
@@ -380,21 +394,39 @@ embed_fwfm_kernel(const EmbedParams p) {
         }
     }
 
-    cp_async_wait_all();   // this thread's segments have landed: fix them up in place
+    DFW_CLK(3);
+    cp_async_wait_all();
     if (any_qr || num > 0) {
-        if (vec2) fixup_rows<2, FT, KT>(g, any_qr); else fixup_rows<1, FT, KT>(g, any_qr);
+        __syncthreads();   // every thread's pieces have landed: fix rows up in place
+        fixup_rows<FT, KT>(g, any_qr);
     }
     __syncthreads();   // E block complete
+    DFW_CLK(4);
 
     // ------------------------------------------------------------------ phase C: stream E out
     if (p.E) {
-        const int ld = (int)p.ldE;
-        float* dst = p.E + b0 * p.ldE;
-        DivStep st(tid, nthreads, ld);
+        if ((p.ldE & 1) == 0 && (reinterpret_cast<uintptr_t>(p.E) & 7) == 0) {      // float2 path (rows 8-byte aligned)
+            const int ld2 = (int)(p.ldE >> 1);
+            float2* dst = reinterpret_cast<float2*>(p.E + b0 * p.ldE);
+            DivStep st(tid, nthreads, ld2);
 #pragma unroll 2
-        for (int i = tid; i < nrows * ld; i += nthreads) {
-            dst[i] = (int)st.r < FK ? sE[st.q * EP + st.r] : 0.f;
-            st.next();
+            for (int i = tid; i < nrows * ld2; i += nthreads) {
+                const int c0 = 2 * (int)st.r;
+                float2 v = make_float2(0.f, 0.f);
+                if (c0 + 1 < FK) v = *reinterpret_cast<const float2*>(sE + st.q * EP + c0);
+                else if (c0 < FK) v.x = sE[st.q * EP + c0];
+                dst[i] = v;
+                st.next();
+            }
+        } else {
+            const int ld = (int)p.ldE;
+            float* dst = p.E + b0 * p.ldE;
+            DivStep st(tid, nthreads, ld);
+#pragma unroll 2
+            for (int i = tid; i < nrows * ld; i += nthreads) {
+                dst[i] = (int)st.r < FK ? sE[st.q * EP + st.r] : 0.f;
+                st.next();
+            }
         }
     }
     if (p.Eb) {
@@ -404,13 +436,15 @@ embed_fwfm_kernel(const EmbedParams p) {
 #pragma unroll 2
         for (int i = tid; i < nrows * ld2; i += nthreads) {
             const int c0 = 2 * (int)st.r;
-            const float lo = c0 < FK ? sE[st.q * EP + c0] : 0.f;
-            const float hi = c0 + 1 < FK ? sE[st.q * EP + c0 + 1] : 0.f;
-            dst[i] = __floats2bfloat162_rn(lo, hi);
+            float2 v = make_float2(0.f, 0.f);
+            if (c0 + 1 < FK) v = *reinterpret_cast<const float2*>(sE + st.q * EP + c0);
+            else if (c0 < FK) v.x = sE[st.q * EP + c0];
+            dst[i] = __floats2bfloat162_rn(v.x, v.y);
             st.next();
         }
     }
 
+    DFW_CLK(5);
     // ------------------------------------------------------------------ phase D: first + second order
     if (owner) {
         const float* myE = sE + smp * EP + kk;   // E[s][f][k] at myE[f*K]
@@ -473,6 +507,7 @@ embed_fwfm_kernel(const EmbedParams p) {
     }
     __syncthreads();
 
+    DFW_CLK(6);
     // ------------------------------------------------------------------ phase E: reduce over k
     if (tid < nrows) {
         float tot = 0.f;
@@ -497,6 +532,11 @@ static int launch_embed(const EmbedParams& p, cudaStream_t st) {
 }
 
 }  // namespace dfw
+
+namespace dfw { static long long* g_clk = nullptr; }
+// Debug tooling (not part of the product ABI): per-CTA clock64() stamps at the phase boundaries of the next
+// embed_fwfm launches are written to `dev_buf` (8 x int64 per CTA); NULL switches it off.
+extern "C" void dfw_debug_set_clock_buffer(void* dev_buf) { dfw::g_clk = static_cast<long long*>(dev_buf); }
 
 extern "C" size_t dfw_shallow_image_bytes(const dfw_model* m) {
     if (!m || m->field_size < 1 || m->embedding_size < 1) return 0;
@@ -537,7 +577,7 @@ extern "C" int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_
     p.fm1 = m->fm_1st; p.bias = m->bias;
     p.E = E_out; p.ldE = ldE; p.Eb = reinterpret_cast<__nv_bfloat16*>(E_bf16_out); p.ldEb = ldEb;
     p.shallow = shallow_out; p.err = (m->flags & DFW_CHECK_INDEX) ? err_word : nullptr;
-    p.B = B; p.F = F; p.num = num; p.K = K; p.flags = m->flags;
+    p.B = B; p.F = F; p.num = num; p.K = K; p.flags = m->flags; p.clk = g_clk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // the two dataset shapes BASELINE.json names get the fully unrolled dense second order
     if (F == 39 && K == 10) return launch_embed<39, 10>(p, st);
