@@ -35,6 +35,7 @@ constexpr int A_CHUNK_BYTES = TILE_M * 128;   // 16 KiB
 constexpr int MAX_KCHUNKS = 8;                // K <= 512
 constexpr int STAGE_ROWS = 256;               // weight rows per stage at most (UMMA N <= 256)
 constexpr int MAX_STAGES = 8;
+constexpr int CLUSTER = 2;                    // CTAs sharing every weight load by TMA multicast
 constexpr int EPI_SPLIT = 3;                  // epilogue warps per TMEM lane quarter (column blocks round-robin)
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
@@ -99,6 +100,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// one load, delivered to the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier (same offset)
+// receives the complete_tx for the bytes that landed in it
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -120,6 +133,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (the weight stage is shared by the cluster)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -185,7 +203,7 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const int L = p.depth;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CLUSTER); }   // a stage is free when BOTH CTAs consumed it
         mbar_init(x_full, 1);
         for (int q = 0; q < 2; ++q) { mbar_init(&acc_full[q], 1); mbar_init(&epi_done[q], 32 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -195,8 +213,12 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     if (warp == 0) tmem_alloc(tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();            // the peer's barriers exist before anything is multicast to it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    const uint32_t crank = cluster_ctarank();
+    // every CTA of a cluster runs the same number of tiles (the weight ring is shared); tiles past the end are dummies
+    const int n_iter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
     // per-layer K (input width, padded to 16) and N (output width padded to 16)
     auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
@@ -212,7 +234,7 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             int parts_per_tile[2] = {0, 0};
             for (int l = 0; l < L; ++l) { parts_per_tile[0] += 1; parts_per_tile[1] += (nparts(layer_n(l)) > 1); }
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; it < n_iter; tile += gridDim.x, ++it) {
                 // the A buffer is free once every epilogue of the previous tile has finished
                 if (it > 0) {
                     for (int q = 0; q < 2; ++q)
@@ -229,8 +251,11 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             mbar_wait(&empty[stage], sphase ^ 1, p.err, 12);
                             // every part is fetched with the same box (rows of part 0); rows past the tensor end are zero-filled
                             // by TMA and still count towards the transaction bytes
+                            // this CTA fetches its half of the box and multicasts it to both CTAs of the cluster
+                            const int half = part_rows(npad, 0) / CLUSTER;
                             mbar_expect_tx(&full[stage], (uint32_t)(part_rows(npad, 0) * 128));
-                            tma_load_2d(sW + (size_t)stage * STAGE_BYTES, &maps.w[l], &full[stage], c * KCH, part_row0(npad, q));
+                            tma_load_2d_mc(sW + (size_t)stage * STAGE_BYTES + (size_t)crank * half * 128, &maps.w[l], &full[stage],
+                                           c * KCH, part_row0(npad, q) + (int)crank * half, (uint16_t)((1u << CLUSTER) - 1));
                             if (++stage == NSTAGE) { stage = 0; sphase ^= 1; }
                         }
                     }
@@ -242,8 +267,7 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (lane == 0) {
             int stage = 0; uint32_t sphase = 0;
             uint32_t epi_cnt[2] = {0, 0};      // epilogue completions of part q that WILL have happened for all layers issued so far
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int it = 0; it < n_iter; ++it) {
                 int prev_np = 0, prev_npad = 0;
                 for (int l = 0; l < L; ++l) {
                     // what the previous layer (or the previous tile's last layer) must have finished, per part
@@ -279,7 +303,7 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             const uint64_t bdesc0 = make_desc_sw128(smem_u32(sW + (size_t)stage * STAGE_BYTES));
                             for (int ks = 0; ks < ksteps; ++ks)      // +32 bytes (16 bf16) along K inside the swizzle atom
                                 umma_bf16(dcol, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), idesc, (c | ks) ? 1u : 0u);
-                            umma_commit(&empty[stage]);               // stage free when these MMAs have read it
+                            umma_commit_mc(&empty[stage], (uint16_t)((1u << CLUSTER) - 1));   // this CTA is done with the stage (both CTAs are told)
                             if (++stage == NSTAGE) { stage = 0; sphase ^= 1; }
                         }
                         umma_commit(&acc_full[q]);                     // accumulators of part q of layer l complete
@@ -297,7 +321,8 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         const int row = q4 * 32 + lane;
         const uint32_t taddr_row = tmem_base + ((uint32_t)(q4 * 32) << 16);
         uint32_t n_acc[2] = {0, 0};
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int eit = 0;
+        for (int tile = blockIdx.x; eit < n_iter; tile += gridDim.x, ++eit) {
             const long long b = (long long)tile * TILE_M + row;
             const bool first_tile = tile == (int)blockIdx.x;
             for (int l = 0; l < L; ++l) {
@@ -391,6 +416,7 @@ mlp_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();            // no CTA exits while its peer may still multicast into it
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -477,7 +503,7 @@ extern "C" int dfw_mlp_bf16(const dfw_model* m, const void* Xb, int64_t ldXb, in
         DFW_REQUIRE(m->Wbf16[l], DFW_E_ARG, "layer %d has no bf16 image (call dfw_pack_mlp_bf16)", l + 1);
         const int npad = tc::pad16(n), kpad = (k + 63) / 64 * 64;
         // all parts of a layer share one map whose box holds the rows of part 0 (the largest)
-        if (int rc = tc::make_map(&maps.w[l], m->Wbf16[l], npad, kpad, kpad, tc::part_rows(npad, 0))) return rc;
+        if (int rc = tc::make_map(&maps.w[l], m->Wbf16[l], npad, kpad, kpad, tc::part_rows(npad, 0) / tc::CLUSTER)) return rc;
         p.widths[l] = n; p.bias[l] = m->b[l];
         k = n;
     }
@@ -510,8 +536,19 @@ extern "C" int dfw_mlp_bf16(const dfw_model* m, const void* Xb, int64_t ldXb, in
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    tc::mlp_tc_kernel<<<grid, tc::NTHREADS, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+    int grid = p.num_tiles < sms ? p.num_tiles : sms;
+    grid = (grid + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
+    if (grid > sms) grid -= tc::CLUSTER;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::NTHREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tc::CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DFW_CUDA_OK(cudaLaunchKernelEx(&cfg, tc::mlp_tc_kernel, maps, p));
     count_launch();
     return check_launch("mlp_tc_kernel");
 }

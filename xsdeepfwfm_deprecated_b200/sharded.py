@@ -1,0 +1,251 @@
+"""Row-sharded embedding tables across the GPUs of one node.
+
+The reference has no distributed code at all; this is the multi-GPU form of its forward
+hot path that BASELINE.json's north_star asks for: the tables are the part that shards, the MLP stays
+batch-data-parallel.
+
+Partitioning (every rank holds the same small state -- MLP, field_cov, fwfm_linear, numeric and small tables --
+and a 1/P slice of every large table):
+
+    row i of a sharded table lives on rank  i mod P  at local row  i div P        (QR tables: the quotient table is
+    sharded on the quotient row, the c-row remainder table is replicated)
+
+Two exchange modes produce bit-identical logits (rows are copied, never summed):
+
+``p2p`` (the product path)
+    Every rank's shard is cudaMalloc'ed by ``dfw_shard_alloc`` and exported with CUDA IPC; each rank maps all peers'
+    shards and puts the P pointers into the field descriptors.  The SAME fused gather kernel then fetches a row with
+    one ``cp.async`` from whichever GPU owns it -- over NVLink 5 / NVSwitch when it is a peer -- straight into the
+    sample's shared-memory block.  Gather, exchange and the FwFM interaction are one kernel: no index exchange, no
+    staging buffers, no collective on the data path.
+
+``nccl`` (the baseline the p2p kernel is measured against)
+    The textbook exchange: route indices to their owners with ``all_to_all_single``, owners gather the requested rows
+    (``dfw_gather_rows``), a second ``all_to_all_single`` returns them, and the fused kernel consumes them as a
+    per-batch table.
+
+``plan_exchange`` / ``route_indices`` / ``assemble_rows`` are pure torch (any device, any backend) so the routing
+logic is unit-tested on CPU with gloo at world_size 2.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .model.DeepFMs import DeepFMs, _stream_ptr
+from .model.QREmbeddingBag import QREmbeddingBag
+
+
+# ------------------------------------------------------------------------------------------------ pure routing logic
+def owner_and_local(idx: torch.Tensor, world: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """owner rank and local row of global row ids under the  i mod P / i div P  partition."""
+    return idx % world, torch.div(idx, world, rounding_mode="floor")
+
+
+def local_rows(rows: int, rank: int, world: int) -> int:
+    """number of rows of a `rows`-row table that rank owns."""
+    return (rows - rank + world - 1) // world if rows > rank else 0
+
+
+def route_indices(idx: torch.Tensor, world: int):
+    """Sort the requests of one rank by owner.  Returns (sorted global ids, send counts per owner, inverse permutation)."""
+    owner = idx % world
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world)
+    inverse = torch.empty_like(order)
+    inverse[order] = torch.arange(order.numel(), device=idx.device)
+    return idx[order], counts, inverse
+
+
+def exchange_rows(idx: torch.Tensor, gather_fn, width: int, group=None, dtype=torch.float32) -> torch.Tensor:
+    """All-to-all row exchange for ONE sharded table: idx (n,) global ids wanted by this rank -> (n, width) rows.
+
+    gather_fn(req_ids) returns the rows of the requested global ids, all of which this rank owns.
+    """
+    world = dist.get_world_size(group)
+    sorted_ids, send_counts, inverse = route_indices(idx, world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    send_l, recv_l = send_counts.tolist(), recv_counts.tolist()
+    req = torch.empty(int(sum(recv_l)), dtype=idx.dtype, device=idx.device)
+    dist.all_to_all_single(req, sorted_ids, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+    rows = gather_fn(req)                                                  # (sum(recv), width): rows I own
+    back = torch.empty(idx.numel(), width, dtype=dtype, device=idx.device)
+    dist.all_to_all_single(back, rows, output_split_sizes=send_l, input_split_sizes=recv_l, group=group)
+    return back[inverse]
+
+
+# ------------------------------------------------------------------------------------------------ the sharded module
+class ShardedDeepFMs(DeepFMs):
+    """``DeepFMs`` whose large second-order tables are row-sharded over the ranks of ``process_group``.
+
+    Build it like ``DeepFMs`` (every rank constructs / loads the FULL state_dict, e.g. from a reference checkpoint),
+    move it to this rank's GPU, then call ``shard_()``: tables with more than ``shard_threshold`` rows are cut down to
+    this rank's slice and the full copies are released.  ``forward`` takes this rank's slice of the batch.
+    """
+
+    def __init__(self, *args, process_group=None, shard_threshold: int = 200, exchange: str = "p2p", **kw):
+        super().__init__(*args, **kw)
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.process_group = process_group
+        self.shard_threshold = shard_threshold
+        self.exchange = exchange
+        self._shards: Dict[int, dict] = {}          # field -> dict(ptrs=[...], own=ptr, rows=..., local_rows=...)
+        self._owned_allocs: List[int] = []
+        self._peer_maps: List[int] = []
+
+    # -- sharding ---------------------------------------------------------------------------------------------
+    def shard_(self):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        lib = _lib.load()
+        group = self.process_group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = self.bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("shard_() needs the module on this rank's CUDA device (no CPU fallback)")
+        if world > _lib.DFW_MAX_RANKS:
+            raise ValueError(f"at most {_lib.DFW_MAX_RANKS} ranks")
+        K = self.embedding_size
+        st = _stream_ptr(dev)
+        handles = []
+        fields = []
+        with torch.cuda.device(dev):
+            for f in range(self.num, self.field_size):
+                emb = self.fm_2nd_embeddings[f]
+                qr = isinstance(emb, QREmbeddingBag)
+                param = emb.weight_q if qr else emb.weight
+                rows = param.shape[0]
+                if world == 1 or rows <= self.shard_threshold:
+                    continue
+                nloc = local_rows(rows, rank, world)
+                ptr = C.c_void_p()
+                _lib.check(lib.dfw_shard_alloc(max(nloc, 1) * K * 4, C.byref(ptr)), "dfw_shard_alloc")
+                self._owned_allocs.append(ptr.value)
+                _lib.check(lib.dfw_shard_rows(param.data_ptr(), rows, K, rank, world, ptr.value, st), "dfw_shard_rows")
+                h = C.create_string_buffer(64)
+                _lib.check(lib.dfw_ipc_export(ptr.value, h), "dfw_ipc_export")
+                handles.append(torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).clone())
+                fields.append((f, rows, nloc, ptr.value, param))
+            torch.cuda.synchronize(dev)
+            if fields:
+                mine = torch.stack(handles).to(dev)                                  # (n_sharded, 64)
+                allh = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(allh, mine, group=group)
+                allh = [h.cpu() for h in allh]
+                for j, (f, rows, nloc, own, param) in enumerate(fields):
+                    ptrs = []
+                    for r in range(world):
+                        if r == rank:
+                            ptrs.append(own)
+                            continue
+                        peer = C.c_void_p()
+                        raw = bytes(allh[r][j].numpy().tobytes())
+                        _lib.check(lib.dfw_ipc_import(raw, C.byref(peer)), "dfw_ipc_import")
+                        self._peer_maps.append(peer.value)
+                        ptrs.append(peer.value)
+                    self._shards[f] = dict(ptrs=ptrs, own=own, rows=rows, local_rows=nloc)
+                    # release the full copy; the parameter keeps its name with zero rows
+                    param.data = torch.empty(0, K, dtype=torch.float32, device=dev)
+            dist.barrier(group=group)
+        self.repack()
+        return self
+
+    def _patch_field_descs(self, descs, plan):
+        if self.exchange != "p2p":
+            return
+        for f, s in self._shards.items():
+            d = descs[f]
+            d.n_ranks = len(s["ptrs"])
+            d.w2 = s["own"]
+            for r, p in enumerate(s["ptrs"]):
+                d.w2_shard[r] = p
+
+    # -- forward ----------------------------------------------------------------------------------------------
+    def forward(self, Xi, Xv, return_prob: bool = False):
+        if self.exchange == "p2p" or not self._shards:
+            return super().forward(Xi, Xv, return_prob)
+        return self._forward_nccl(Xi, Xv, return_prob)
+
+    def _forward_nccl(self, Xi, Xv, return_prob):
+        """Baseline: index all-to-all -> owner gather -> row all-to-all -> fused kernel on per-batch tables."""
+        lib = _lib.load()
+        group = self.process_group
+        world = dist.get_world_size(group)
+        dev = self.bias.device
+        K, B = self.embedding_size, Xi.shape[0]
+        st = _stream_ptr(dev)
+        Xi2 = Xi.clone()
+        arange = torch.arange(B, device=dev, dtype=torch.int64)
+        staged = {}
+        for f, s in self._shards.items():
+            emb = self.fm_2nd_embeddings[f]
+            c = emb.num_collisions if isinstance(emb, QREmbeddingBag) else 1
+            ids = Xi[:, f - self.num, 0]
+            row_ids = torch.div(ids, c, rounding_mode="floor") if c > 1 else ids
+
+            def gather(req, s=s):
+                out = torch.empty(req.numel(), K, dtype=torch.float32, device=dev)
+                if req.numel():
+                    _lib.check(lib.dfw_gather_rows(s["own"], s["local_rows"], K, req.data_ptr(), req.numel(), world,
+                                                   out.data_ptr(), st), "dfw_gather_rows")
+                return out
+
+            rows = exchange_rows(row_ids.contiguous(), gather, K, group=group)           # (B, K) quotient/plain rows
+            staged[f] = rows
+            # the fused kernel reads the staged rows as a B-row table: index b (times c plus the remainder for QR)
+            Xi2[:, f - self.num, 0] = arange * c + (ids % c if c > 1 else 0)
+        return self._forward_with_tables(Xi2, Xv, staged, B, return_prob)
+
+    def _forward_with_tables(self, Xi2, Xv, staged, B, return_prob):
+        lib = _lib.load()
+        plan = self._get_plan()
+        dev = plan.device
+        F = self.field_size
+        descs = (_lib.FieldDesc * F).from_buffer_copy(bytes(plan.fields_dev.cpu().numpy().tobytes()))
+        for f, rows in staged.items():
+            emb = self.fm_2nd_embeddings[f]
+            c = emb.num_collisions if isinstance(emb, QREmbeddingBag) else 1
+            descs[f].w2 = rows.data_ptr()
+            descs[f].rows = B * c
+            descs[f].n_ranks = 0
+        fields = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        m = _lib.Model.from_buffer_copy(bytes(plan.model))
+        m.fields = fields.data_ptr()
+        m.shallow_image = None                       # rebuilt from the temporary descriptors inside dfw_forward
+        prec = _lib.PRECISIONS[self.precision]
+        plan.ensure_image(self, self.precision)
+        for l in range(self.h_depth if self.use_deep else 0):
+            m.Wbf16[l] = plan.model.Wbf16[l]
+            m.csr[l] = plan.model.csr[l]
+        ref = C.byref(m)
+        nbytes = lib.dfw_forward_workspace_bytes(ref, B, prec)
+        ws = torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        prob = torch.empty(B, dtype=torch.float32, device=dev) if return_prob else None
+        with torch.cuda.device(dev):
+            rc = lib.dfw_forward(ref, Xi2.data_ptr(), Xi2.stride(0), Xi2.stride(1), Xv.data_ptr() if self.num else None,
+                                 Xv.stride(0), Xv.stride(1), B, prec, ws.data_ptr(), ws.numel(), logits.data_ptr(),
+                                 prob.data_ptr() if prob is not None else None, None, _stream_ptr(dev))
+        _lib.check(rc, "dfw_forward")
+        torch.cuda.current_stream(dev).synchronize()      # `staged`, `fields`, `ws` must outlive the kernels
+        return (logits, prob) if return_prob else logits
+
+    def release(self):
+        """Unmap peers and free this rank's shards (call on every rank before exit)."""
+        lib = _lib.load()
+        self._plan = None
+        for p in self._peer_maps:
+            lib.dfw_ipc_close(p)
+        self._peer_maps = []
+        if dist.is_initialized():
+            dist.barrier(group=self.process_group)
+        for p in self._owned_allocs:
+            lib.dfw_shard_free(p)
+        self._owned_allocs = []
+        self._shards = {}
