@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DFW_ABI_VERSION 1
+#define DFW_ABI_VERSION 2
 #define DFW_MAX_DEPTH 8
 #define DFW_MAX_FIELDS 64
 #define DFW_MAX_K 32
@@ -64,6 +64,9 @@ extern "C" {
 #define DFW_PREC_FP32 0      /* CUDA-core fp32 MLP: the 1e-5 parity path                  */
 #define DFW_PREC_BF16 1      /* tcgen05 bf16 MLP, fp32 accumulate: the looser-bound path  */
 #define DFW_PREC_FP32_CSR 2  /* fp32 CSR MLP for magnitude-pruned weights                 */
+#define DFW_PREC_BF16X3 3    /* tcgen05 MLP on split operands x = hi + lo (two bf16): W_hi X_hi + W_hi X_lo + W_lo X_hi,
+                                fp32 accumulate -- inside the fp32 parity bound (1e-5 * max|logit|) at tensor-core speed;
+                                shapes outside the fused kernel's limits run the CUDA-core fp32 MLP instead             */
 
 /* One embedding field (reference: one entry of fm_2nd_embeddings / fm_1st_embeddings,
  * model/DeepFMs.py:197-210, 1066-1091).  An array of F of these lives in DEVICE memory.
@@ -109,7 +112,8 @@ typedef struct dfw_model {
     const float* W[DFW_MAX_DEPTH];  /* net_1_linear_l.weight (out, in) row-major fp32        */
     const float* b[DFW_MAX_DEPTH];  /* net_1_linear_l.bias                                   */
     const float* fc;                /* (N) net_1_fc.weight                                   */
-    const void* Wbf16[DFW_MAX_DEPTH]; /* dfw_pack_mlp_bf16 image of W[l], or NULL            */
+    const void* Wbf16[DFW_MAX_DEPTH]; /* dfw_pack_mlp_bf16 image of W[l] (= hi part), or NULL */
+    const void* Wbf16_lo[DFW_MAX_DEPTH]; /* lo part bf16(W - hi) from dfw_pack_mlp_bf16_split (DFW_PREC_BF16X3), or NULL */
     dfw_csr csr[DFW_MAX_DEPTH];     /* dfw_csr_build image of W[l] (row_ptr NULL if absent)  */
     const void* shallow_image;      /* dfw_pack_shallow image (DEVICE), or NULL: dfw_forward then packs per call */
 } dfw_model;
@@ -174,6 +178,8 @@ int dfw_finish_shallow(const float* shallow, int64_t B, float* logits_out, float
  * dfw_pack_mlp_bf16_bytes.  Runs on the device (no host sync). */
 size_t dfw_pack_mlp_bf16_bytes(int32_t out_dim, int32_t in_dim);
 int dfw_pack_mlp_bf16(const float* W, int32_t out_dim, int32_t in_dim, void* dst, void* stream);
+/* hi = bf16(W) and lo = bf16(W - hi) images (same layout as dfw_pack_mlp_bf16; either destination may be NULL). */
+int dfw_pack_mlp_bf16_split(const float* W, int32_t out_dim, int32_t in_dim, void* dst_hi, void* dst_lo, void* stream);
 /* CSR image of one pruned Linear weight.  Two device passes: count (fills row_ptr, returns nnz through
  * a device word the caller reads) and fill.  `row_ptr` has out_dim+1 entries. */
 int dfw_csr_count(const float* W, int32_t out_dim, int32_t in_dim, int32_t* row_ptr, void* stream);
@@ -189,6 +195,13 @@ int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int6
                 const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
                 void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
                 int32_t* err_word, void* stream);
+/* The single-kernel form of the forward (gather + FwFM on the CUDA cores, MLP on tcgen05, logit/sigmoid epilogue;
+ * DFW_PREC_BF16 or DFW_PREC_BF16X3).  dfw_forward takes this route by itself whenever dfw_fused_supported(m, precision);
+ * needs m->shallow_image and the bf16 weight images.  No workspace. */
+int dfw_fused_supported(const dfw_model* m, int precision);
+int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
+                      const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
+                      float* logits_out, float* prob_out, int32_t* err_word, void* stream);
 /* Same with HOST inputs/outputs (what eval_by_batch / predict_proba do around forward,
  * model/DeepFMs.py:771-777): H2D of xi/xv (contiguous) into the staging area at the start of the
  * workspace, forward, sigmoid, D2H of `prob_host` and/or `logits_host`, then SYNCHRONISES `stream`.

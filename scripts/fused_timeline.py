@@ -1,0 +1,41 @@
+"""Debug tool: per-CTA timeline of fused_forward_kernel (clock64 stamps), config 2, B=4096 by default.
+
+    python scripts/fused_timeline.py [B] [bf16|bf16x3]
+"""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from oracle import synth
+from xsdeepfwfm_deprecated_b200 import _lib
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
+m = bench.make_model(dev, prec, synth.CRITEO_PAPER)
+plan = m._get_plan(); plan.ensure_image(m, prec)
+Xi, Xv = bench.make_batches(dev, synth.CRITEO_PAPER, B, 4, seed=0)
+out = torch.zeros(B, device=dev)
+nc = min((B + 31) // 32, 148)
+clk = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
+fn = lib.dfw_debug_set_fused_clock_buffer; fn.argtypes = [ctypes.c_void_p]; fn.restype = None
+st = torch.cuda.current_stream().cuda_stream
+def run(j=0):
+    rc = lib.dfw_forward_fused(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), 13, 1, B, _lib.PRECISIONS[prec],
+                               out.data_ptr(), None, None, st)
+    _lib.check(rc, "dfw_forward_fused")
+for j in range(3): run(j)
+torch.cuda.synchronize()
+fn(clk.data_ptr()); run(3); torch.cuda.synchronize(); fn(None)
+c = clk.cpu().numpy().reshape(148, 32)[:nc].astype(np.float64)
+t0 = c[:, 0:1]          # MMA thread reaches the x_ready wait
+rel = c - t0
+names = {20: "gather done (E block)", 21: "X0 converted", 1: "x_ready seen by MMA", 22: "shallow done", 16: "tile done"}
+for l in range(3):
+    names[2 + l] = f"L{l+1} all MMAs issued"
+    names[8 + 2 * l] = f"L{l+1} first acc ready"
+    names[9 + 2 * l] = f"L{l+1} epilogue done"
+order = [20, 21, 1, 8, 2, 9, 10, 3, 11, 12, 4, 13, 22, 16]
+print(f"B={B} {prec}: cycles relative to the MMA thread's start (median over {nc} CTAs / min / max)")
+for k in order:
+    print(f"  {names[k]:24s} {np.median(rel[:, k]):9.0f} {rel[:, k].min():9.0f} {rel[:, k].max():9.0f}")

@@ -292,3 +292,79 @@ def test_bf16_equals_fp32_on_bf16_representable_problem():
     ref = closed_form.forward(cfg, w, Xi, Xv)["logit"]
     a = run(to_cuda(cfg, w, precision="bf16"), Xi, Xv)
     assert np.abs(a - ref).max() <= logit_tol(ref, FP32_REL)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bf16x3: the fused single-kernel forward on split bf16 operands (csrc/fused_tc.cu).  It claims the fp32 bound.
+@pytest.mark.parametrize("name", [n for n in CASES if load_case(n)["cfg"].use_deep])
+def test_golden_logits_bf16x3(name):
+    c = load_case(name)
+    m = to_cuda(c["cfg"], c["weights"], precision="bf16x3")
+    got = run(m, c["Xi"], c["Xv"])
+    assert got.shape == c["logits"].shape and got.dtype == np.float32
+    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL)
+    ref64 = closed_form.forward(c["cfg"], c["weights"], c["Xi"], c["Xv"])["logit"]
+    assert np.abs(got - ref64).max() <= logit_tol(ref64, FP32_REL)
+
+
+def test_fused_kernel_takes_the_baseline_shapes():
+    """The Criteo and Twitter shapes of BASELINE.json must run as the single fused kernel, not the staged path."""
+    from xsdeepfwfm_deprecated_b200 import _lib
+    lib = _lib.load()
+    for name in ("deepfwfm_fwlw", "twitter_shape", "qr_mult_fwlw", "pruned", "k7", "k16", "deepfwfm_h4"):
+        c = load_case(name)
+        for precision in ("bf16", "bf16x3"):
+            m = to_cuda(c["cfg"], c["weights"], precision=precision)
+            plan = m._get_plan()
+            plan.ensure_image(m, precision)
+            assert lib.dfw_fused_supported(plan.model_ref, _lib.PRECISIONS[precision]) == 1, (name, precision)
+            l0 = lib.dfw_launch_count()
+            run(m, c["Xi"], c["Xv"])
+            assert lib.dfw_launch_count() - l0 == 1, (name, precision)
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 32, 33, 127, 129, 1000, 4097, 20000])
+def test_bf16x3_ragged_and_multi_tile(B):
+    """Partial 32-sample tiles, partial clusters, and more tiles than SMs (persistent loop, barrier phase wrap)."""
+    c = load_case("deepfwfm_fwlw")
+    cfg = c["cfg"]
+    Xi, Xv = synth.make_inputs(cfg, B, seed=B)
+    ref = closed_form.forward(cfg, c["weights"], Xi, Xv)
+    for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", BF16_REL, 2e-2 * np.abs(ref["deep"]).max())):
+        got = run(to_cuda(cfg, c["weights"], precision=precision), Xi, Xv)
+        assert got.shape == (B,)
+        assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], rel) + extra, precision
+
+
+def test_config2_full_size_batch_4096_bf16x3():
+    """BASELINE config 2 at full size on the fused kernel: fp32 bound, batch-order equivariance, sample independence."""
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    Xi, Xv = synth.make_inputs(cfg, 4096, seed=0)
+    ref = closed_form.forward(cfg, w, Xi, Xv)
+    m = to_cuda(cfg, w, precision="bf16x3")
+    got = run(m, Xi, Xv)
+    assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], FP32_REL)
+    # the deep term alone (what the split operands touch), against the fp64 oracle
+    shallow = ref["first"] + ref["second"] + float(w["bias"][0])
+    assert np.abs((got - shallow) - ref["deep"]).max() <= 5e-5 * np.abs(ref["deep"]).max() + 1e-5 * np.abs(ref["logit"]).max()
+    perm = np.random.default_rng(0).permutation(4096)
+    assert np.array_equal(run(m, Xi[perm], Xv[perm]), got[perm])
+    assert np.array_equal(run(m, Xi[:100], Xv[:100]), got[:100])
+    with torch.no_grad():
+        logits, prob = m(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda(), return_prob=True)
+    assert torch.allclose(prob, torch.sigmoid(logits), atol=2e-7, rtol=1e-6)
+
+
+def test_config3_pruned_and_config5_twitter_bf16x3():
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = prune.one_shot_prune(synth.make_weights(cfg, seed=42), 0.9, 0.444, 1.0)
+    Xi, Xv = synth.make_inputs(cfg, 4096, seed=3, dist="zipf")
+    ref = closed_form.forward(cfg, w, Xi, Xv)["logit"]
+    got = run(to_cuda(cfg, w, precision="bf16x3"), Xi, Xv)
+    assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL)
+    c = load_case("twitter_shape")
+    Xi, Xv = synth.make_inputs(c["cfg"], 3000, seed=8, xv="unit")
+    ref = closed_form.forward(c["cfg"], c["weights"], Xi, Xv)["logit"]
+    got = run(to_cuda(c["cfg"], c["weights"], precision="bf16x3"), Xi, Xv)
+    assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL)

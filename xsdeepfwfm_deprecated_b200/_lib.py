@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdeepfwfm_sm100a.so")
 
-DFW_ABI_VERSION = 1
+DFW_ABI_VERSION = 2
 DFW_MAX_DEPTH = 8
 DFW_MAX_FIELDS = 64
 DFW_MAX_K = 32
@@ -19,8 +19,8 @@ DFW_MAX_RANKS = 8
 
 USE_FWFM, USE_FWLW, USE_LW, USE_DEEP, CHECK_INDEX = 1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 8
 TABLE_PLAIN, TABLE_QR_MULT, TABLE_QR_ADD = 0, 1, 2
-PREC_FP32, PREC_BF16, PREC_FP32_CSR = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32_csr": PREC_FP32_CSR}
+PREC_FP32, PREC_BF16, PREC_FP32_CSR, PREC_BF16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32_csr": PREC_FP32_CSR, "bf16x3": PREC_BF16X3}
 
 
 class FieldDesc(C.Structure):
@@ -42,7 +42,8 @@ class Model(C.Structure):
                 ("fields", C.c_void_p), ("fwfm_linear", C.c_void_p), ("fm_1st", C.c_void_p),
                 ("field_cov", C.c_void_p), ("bias", C.c_void_p),
                 ("W", C.c_void_p * DFW_MAX_DEPTH), ("b", C.c_void_p * DFW_MAX_DEPTH), ("fc", C.c_void_p),
-                ("Wbf16", C.c_void_p * DFW_MAX_DEPTH), ("csr", Csr * DFW_MAX_DEPTH),
+                ("Wbf16", C.c_void_p * DFW_MAX_DEPTH), ("Wbf16_lo", C.c_void_p * DFW_MAX_DEPTH),
+                ("csr", Csr * DFW_MAX_DEPTH),
                 ("shallow_image", C.c_void_p)]
 
 
@@ -65,10 +66,13 @@ SYMBOLS = {
     "dfw_finish_shallow": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "dfw_pack_mlp_bf16_bytes": (_sz, [_i32, _i32]),
     "dfw_pack_mlp_bf16": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "dfw_pack_mlp_bf16_split": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "dfw_csr_count": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "dfw_csr_fill": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dfw_forward_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_forward": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _i64, _i64, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "dfw_fused_supported": (C.c_int, [_MP, C.c_int]),
+    "dfw_forward_fused": (C.c_int, [_MP, _vp, _i64, _i64, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp]),
     "dfw_forward_host_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_forward_host": (C.c_int, [_MP, _vp, _vp, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp]),
     "dfw_shard_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),

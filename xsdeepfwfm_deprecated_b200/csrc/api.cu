@@ -1,5 +1,6 @@
 // C-ABI glue of libdeepfwfm_sm100a: error strings, device check, whole-forward entry points, shard helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dfw_common.cuh"
@@ -105,8 +106,8 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");
     if (B == 0) return 0;
     DFW_REQUIRE(logits_out || prob_out, DFW_E_ARG, "no output requested");
-    DFW_REQUIRE(precision == DFW_PREC_FP32 || precision == DFW_PREC_BF16 || precision == DFW_PREC_FP32_CSR,
-                DFW_E_ARG, "unknown precision %d", precision);
+    DFW_REQUIRE(precision == DFW_PREC_FP32 || precision == DFW_PREC_BF16 || precision == DFW_PREC_FP32_CSR ||
+                precision == DFW_PREC_BF16X3, DFW_E_ARG, "unknown precision %d", precision);
     const FwdLayout L = fwd_layout(m, B, precision);
     DFW_REQUIRE(workspace && workspace_bytes >= L.total, DFW_E_WORKSPACE, "forward workspace too small: %zu < %zu",
                 workspace_bytes, L.total);
@@ -116,14 +117,19 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     float* E = (deep && precision != DFW_PREC_BF16) ? reinterpret_cast<float*>(ws + L.oE) : nullptr;
     void* Eb = (deep && precision == DFW_PREC_BF16) ? static_cast<void*>(ws + L.oEb) : nullptr;
     float* shallow = reinterpret_cast<float*>(ws + L.oShallow);
-    if (!err_word) err_word = reinterpret_cast<int32_t*>(ws + L.oErr);
     dfw_model local;
+    if (!err_word) err_word = reinterpret_cast<int32_t*>(ws + L.oErr);
     if (!m->shallow_image) {   // "always fresh" mode: rebuild the shallow image from the live parameters per call
         local = *m;
         local.shallow_image = ws + L.oImg;
         if (int rc = dfw_pack_shallow(m, ws + L.oImg, stream)) return rc;
         m = &local;
     }
+    // one kernel for the whole forward when the tensor-core form fits the model's shapes
+    static const bool no_fused = getenv("DFW_NO_FUSED") != nullptr;
+    if (deep && !no_fused && (precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3) && dfw_fused_supported(m, precision))
+        return dfw_forward_fused(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, precision, logits_out,
+                                 prob_out, err_word, stream);
     if (int rc = dfw_embed_fwfm(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, E, L.ldE, Eb, L.ldEb,
                                 shallow, err_word, stream))
         return rc;
@@ -132,6 +138,7 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     const size_t mbytes = workspace_bytes - L.oMlp;
     if (precision == DFW_PREC_BF16) return dfw_mlp_bf16(m, Eb, L.ldEb, B, shallow, mws, mbytes, logits_out, prob_out, stream);
     if (precision == DFW_PREC_FP32_CSR) return dfw_mlp_csr(m, E, L.ldE, B, shallow, mws, mbytes, logits_out, prob_out, stream);
+    // DFW_PREC_FP32, and DFW_PREC_BF16X3 on shapes the fused kernel does not take: CUDA-core fp32 (stricter, slower)
     return dfw_mlp_fp32(m, E, L.ldE, B, shallow, mws, mbytes, logits_out, prob_out, stream);
 }
 

@@ -9,7 +9,7 @@
 //   header | U = strict upper triangle of (R + R^T)/2 stored by columns, padded to float4 (FM: ones) |
 //   compacted list of live pairs (for pruned R) | fwlw weights with fm_1st folded in | field descriptors
 //
-// embed_fwfm_kernel, per batch:
+// embed_fwfm_kernel, per batch (device code shared with the fused forward kernel: embed_device.cuh):
 //   CTA  = 16 samples x K columns: thread t owns (sample t & 15, column t >> 4) in phase D
 //   SMEM = shallow image copy + the 16 x (F*K) embedding block of the CTA's samples (pitch = 2 mod 32
 //          floats: the column reads of a warp -- 16 samples x 2 columns -- hit 32 distinct banks, rows stay
@@ -27,77 +27,26 @@
 //   phase E  fixed-order reduction over k -> shallow[b] = first + second + bias
 //
 // Bytes per sample the algorithm needs (Criteo, fwlw): 26*8 + 13*4 + 26*40 + 4 = 1304.
-#include "dfw_common.cuh"
+#include "embed_device.cuh"
 
 namespace dfw {
 
-constexpr int kS = 16;  // samples per CTA
-
-struct EmbedParams {
-    const unsigned char* image;
-    const int64_t* xi; int64_t xi_sb, xi_sc;
-    const float* xv; int64_t xv_sb, xv_sc;
-    const float* fm1; const float* bias;
-    float* E; int64_t ldE; __nv_bfloat16* Eb; int64_t ldEb; float* shallow; int32_t* err;
-    int64_t B; int F, num, K; unsigned flags;
-    long long* clk;   // optional per-CTA phase timestamps (debug tooling, see dfw_debug_set_clock_buffer)
-};
-
-struct PairEnt { uint32_t ij; float u; };  // ij = (i*K) | (j*K) << 16
-struct ImgHeader { int32_t live, n_list, any_special, misaligned; };   // any_special: some table is QR or rank-sharded
-
-__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
-// column j of the strict upper triangle holds U_0j .. U_(j-1)j, padded to a multiple of 4 floats:
-// offset = sum_{c=1}^{j-1} pad4(c) = 4 (m+1)(2m + r) with j-1 = 4m + r
-__host__ __device__ constexpr int ucol_off(int j) {
-    const int n = j - 1, m = n >> 2, r = n & 3;
-    return n <= 0 ? 0 : 4 * (m + 1) * (2 * m + r);
-}
-__host__ __device__ constexpr int usize(int F) { return ucol_off(F); }
-__host__ __device__ constexpr int e_pitch(int FK) { return FK + ((34 - (FK & 31)) & 31); }   // >= FK, == 2 mod 32
-__host__ __device__ constexpr size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
-
-struct ImgLayout { size_t oHdr, oU, oPairs, oWl, oFields, total; };
-__host__ __device__ inline ImgLayout img_layout(int F, int K) {
-    ImgLayout L;
-    size_t o = 0;
-    L.oHdr = o;    o += 16;
-    L.oU = o;      o += up16(sizeof(float) * (usize(F) + 4));
-    L.oPairs = o;  o += up16(sizeof(PairEnt) * (size_t)(F * (F - 1) / 2) + 8);
-    L.oWl = o;     o += up16(sizeof(float) * F * K);
-    L.oFields = o; o += up16(sizeof(dfw_field_desc) * F);
-    L.total = o;
-    return L;
-}
+constexpr int kS = 16;  // samples per CTA of the stand-alone kernel
 
 struct SmemLayout { int EP; size_t oImg, oE, oPart, oIdx, oXv, total; };
 __host__ __device__ inline SmemLayout smem_layout(int F, int K, int num) {
     SmemLayout L;
-    const int C = F - num;
-    L.EP = e_pitch(F * K);
+    const TileSizes t = tile_sizes(F, K, num, kS);
+    L.EP = t.EP;
     size_t o = 0;
     L.oImg = o;  o += img_layout(F, K).total;
-    L.oE = o;    o += up16(sizeof(float) * kS * L.EP);
-    L.oPart = o; o += up16(sizeof(float) * K * kS);
-    L.oIdx = o;  o += up16(sizeof(int32_t) * kS * (C > 0 ? C : 1));
-    L.oXv = o;   o += up16(sizeof(float) * kS * (num > 0 ? num : 1));
+    L.oE = o;    o += t.bE;
+    L.oPart = o; o += t.bPart;
+    L.oIdx = o;  o += t.bIdx;
+    L.oXv = o;   o += t.bXv;
     L.total = o;
     return L;
 }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ pack kernel
 struct PackParams {
@@ -168,240 +117,36 @@ __global__ void __launch_bounds__(256) pack_shallow_kernel(const PackParams p) {
     if (tid == 0) { hdr->live = s_live; hdr->any_special = s_qr; hdr->misaligned = s_mis; }
 }
 
-// ------------------------------------------------------------------------------------------ gather helpers
-// Where the stored row of category `idx` of a field lives: quotient-remainder split
-// (model/QREmbeddingBag.py:157-158) and rank sharding (owner = row mod P, local row = row div P).
-__device__ __forceinline__ const float* locate_row(const dfw_field_desc& fd, int32_t idx, int K) {
-    uint32_t row = (uint32_t)idx;
-    if (fd.qr_op != DFW_TABLE_PLAIN) row = (uint32_t)idx / (uint32_t)fd.collisions;
-    const float* base = fd.w2;
-    if (fd.n_ranks > 1) {
-        const uint32_t P = (uint32_t)fd.n_ranks;
-        const uint32_t local = row / P;
-        base = fd.w2_shard[row - local * P];
-        row = local;
-    }
-    return base + (int64_t)row * K;
-}
-
-// (q, r) = divmod(start + n * stride, d) advanced without divisions
-struct DivStep {
-    uint32_t q, r, dq, dr, d;
-    __device__ __forceinline__ DivStep(uint32_t start, uint32_t stride, uint32_t d_) : d(d_) {
-        q = start / d; r = start - q * d; dq = stride / d; dr = stride - dq * d;
-    }
-    __device__ __forceinline__ void next() { q += dq; r += dr; if (r >= d) { r -= d; ++q; } }
-};
-
-struct GatherCtx {
-    const dfw_field_desc* sF; const int32_t* sIdx; const float* sXv; float* sE;
-    int F, K, num, C, EP, nrows, tid, nthreads;
-};
-
-// Adjacent lanes take adjacent 8-byte (SEGW = 2: all row bases 8-byte aligned, K even) or 4-byte pieces of the
-// same row, so one warp instruction touches ~7 rows / cache lines instead of 32 (LSU wavefronts are the cost
-// of a gather); all pieces of the block are in flight together, global -> SMEM without register staging.
-// PLAIN = no table of the model is QR or rank-sharded: branch-free body (row = w2 + idx * K).
-template <int SEGW, int FT, int KT, bool PLAIN>
-__device__ __forceinline__ void issue_rows(const GatherCtx& g) {
-    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
-    const int K = KT > 0 ? KT : g.K;
-    const uint32_t nV = (uint32_t)(K / SEGW);
-    const uint32_t total = (uint32_t)g.nrows * F * nV;
-#pragma unroll 4
-    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t row = e / nV, k = (e - row * nV) * SEGW;
-        const uint32_t s = row / F, f = row - s * F;
-        const int32_t idx = (int)f < g.num ? 0 : g.sIdx[s * g.C + (f - g.num)];
-        const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
-        float* dst = g.sE + s * g.EP + f * K + k;
-        if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
-    }
-}
-
-// quotient (*|+) remainder row for QR tables (model/QREmbeddingBag.py:169-172), times Xv for numeric fields
-// (model/DeepFMs.py:334): one fp32 operation each, applied after the block's copies have landed.
-template <int FT, int KT>
-__device__ __forceinline__ void fixup_rows(const GatherCtx& g, bool any_qr) {
-    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
-    const int K = KT > 0 ? KT : g.K;
-    const uint32_t total = (uint32_t)g.nrows * F;
-#pragma unroll 1
-    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t s = e / F, f = e - s * F;
-        const bool numeric = (int)f < g.num;
-        if (!any_qr && !numeric) continue;
-        const dfw_field_desc& fd = g.sF[f];
-        const int op = fd.qr_op;
-        if (op == DFW_TABLE_PLAIN && !numeric) continue;
-        float* dst = g.sE + s * g.EP + f * K;
-        const float x = numeric ? g.sXv[s * g.num + f] : 1.0f;
-        const float* rrow = nullptr;
-        if (op != DFW_TABLE_PLAIN) {
-            const int32_t idx = numeric ? 0 : g.sIdx[s * g.C + (f - g.num)];
-            const uint32_t c = (uint32_t)fd.collisions;
-            rrow = fd.w2_r + ((uint32_t)idx - ((uint32_t)idx / c) * c) * K;
-        }
-#pragma unroll 2
-        for (int k = 0; k < K; ++k) {
-            float v = dst[k];
-            if (op == DFW_TABLE_QR_MULT) v *= __ldg(rrow + k);
-            else if (op == DFW_TABLE_QR_ADD) v += __ldg(rrow + k);
-            if (numeric) v *= x;
-            dst[k] = v;
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------ main kernel
 // FT/KT > 0: compile-time field count / embedding width (dense unrolled second order available).
+// CTA = 16 samples x K columns: thread t owns (sample t & 15, column t >> 4) in phase D.
 template <int FT, int KT>
 __global__ void __launch_bounds__(FT > 0 ? ((kS * KT + 31) / 32) * 32 : 512)
 embed_fwfm_kernel(const EmbedParams p) {
     const int F = FT > 0 ? FT : p.F;
     const int K = KT > 0 ? KT : p.K;
-    const int num = p.num;
-    const int C = F - num;
     const int FK = F * K;
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
-    const int smp = tid & (kS - 1);          // sample within the CTA (phase D)
-    const int kk = tid >> 4;                 // embedding column owned in phase D (valid if < K)
     const int64_t b0 = (int64_t)blockIdx.x * kS;
     const int nrows = (int)min((int64_t)kS, p.B - b0);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemLayout L = smem_layout(F, K, num);
-    const ImgLayout IL = img_layout(F, K);
-    unsigned char* sImg = smem_raw + L.oImg;
-    const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg + IL.oHdr);
-    const float* sU = reinterpret_cast<const float*>(sImg + IL.oU);
-    const PairEnt* sPairs = reinterpret_cast<const PairEnt*>(sImg + IL.oPairs);
-    const float* sWl = reinterpret_cast<const float*>(sImg + IL.oWl);
-    const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + IL.oFields);
-    float* sE = reinterpret_cast<float*>(smem_raw + L.oE);
-    float* sPart = reinterpret_cast<float*>(smem_raw + L.oPart);
-    int32_t* sIdx = reinterpret_cast<int32_t*>(smem_raw + L.oIdx);
-    float* sXv = reinterpret_cast<float*>(smem_raw + L.oXv);
+    const SmemLayout L = smem_layout(F, K, p.num);
+    TileSmem sm;
+    sm.img = smem_raw + L.oImg;
+    sm.E = reinterpret_cast<float*>(smem_raw + L.oE);
+    sm.part = reinterpret_cast<float*>(smem_raw + L.oPart);
+    sm.idx = reinterpret_cast<int32_t*>(smem_raw + L.oIdx);
+    sm.xv = reinterpret_cast<float*>(smem_raw + L.oXv);
+    sm.EP = L.EP;
+    const float* sE = sm.E;
     const int EP = L.EP;
-    const bool fwlw = p.flags & DFW_USE_FWLW;
+    long long* clk = p.clk ? p.clk + blockIdx.x * 8 : nullptr;
+    if (clk && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); clk[7] = (long long)t; }
 
-#define DFW_CLK(slot) do { if (p.clk && tid == 0) p.clk[blockIdx.x * 8 + (slot)] = clock64(); } while (0)
-    if (p.clk && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.clk[blockIdx.x * 8 + 7] = (long long)t; }
-    DFW_CLK(0);
-    // ------------------------------------------------------------------ phase A
-    // batch inputs first: they come from DRAM; the shallow image is L2-resident model state
-    constexpr int kMaxIdx = 4, kMaxXv = 2;
-    int64_t myidx[kMaxIdx];
-    int mycol[kMaxIdx];
-    float myxv[kMaxXv];
-    const int nIdx = kS * C, nXv = kS * num;
-    {
-        DivStep st(tid, nthreads, C > 0 ? C : 1);
-#pragma unroll
-        for (int r = 0; r < kMaxIdx; ++r) {
-            myidx[r] = 0; mycol[r] = (int)st.r;
-            if (tid + r * nthreads < nIdx && (int)st.q < nrows) myidx[r] = p.xi[(b0 + st.q) * p.xi_sb + st.r * p.xi_sc];
-            st.next();
-        }
-        DivStep sv(tid, nthreads, num > 0 ? num : 1);
-#pragma unroll
-        for (int r = 0; r < kMaxXv; ++r) {
-            myxv[r] = 0.f;
-            if (tid + r * nthreads < nXv && (int)sv.q < nrows) myxv[r] = p.xv[(b0 + sv.q) * p.xv_sb + sv.r * p.xv_sc];
-            sv.next();
-        }
-    }
-#pragma unroll 2
-    for (uint32_t i = tid; i < (uint32_t)(IL.total >> 4); i += nthreads) cp_async16(sImg + 16 * i, p.image + 16 * i);
-    cp_async_wait_all();
-    __syncthreads();   // image visible (row counts for the bounds check)
-    DFW_CLK(1);
-
-#pragma unroll
-    for (int r = 0; r < kMaxIdx; ++r) {
-        const int e = tid + r * nthreads;
-        if (e < nIdx) {
-            const int c = mycol[r];
-            int64_t idx = myidx[r];
-            if (idx < 0 || idx >= sF[num + c].rows) {   // defined behaviour instead of a wild read
-                if (p.err) atomicExch(p.err, 1 + num + c);
-                idx = 0;
-            }
-            sIdx[e] = (int32_t)idx;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kMaxXv; ++r) {
-        const int e = tid + r * nthreads;
-        if (e < nXv) sXv[e] = myxv[r];
-    }
-#pragma unroll 1
-    for (uint32_t e = tid + kMaxXv * nthreads; e < (uint32_t)nXv; e += nthreads) {      // small CTAs only
-        const uint32_t s = e / (uint32_t)num, f = e - s * num;
-        sXv[e] = (int)s < nrows ? p.xv[(b0 + s) * p.xv_sb + f * p.xv_sc] : 0.f;
-    }
-#pragma unroll 1
-    for (uint32_t e = tid + kMaxIdx * nthreads; e < (uint32_t)nIdx; e += nthreads) {    // small CTAs only
-        const uint32_t s = e / (uint32_t)C, c = e - s * C;
-        int64_t idx = (int)s < nrows ? p.xi[(b0 + s) * p.xi_sb + c * p.xi_sc] : 0;
-        if (idx < 0 || idx >= sF[num + c].rows) {
-            if (p.err) atomicExch(p.err, 1 + num + c);
-            idx = 0;
-        }
-        sIdx[e] = (int32_t)idx;
-    }
-    __syncthreads();   // indices + dense values visible
-    DFW_CLK(2);
-
-    const int P = F * (F - 1) / 2;
-    const bool use_list = (FT == 0) || (hdr->live * 6 < P);
-    const bool any_qr = hdr->any_special != 0;
-    const bool vec2 = hdr->misaligned == 0 && (K % 2 == 0);    // all row bases 8-byte aligned
-
-    // ------------------------------------------------------------------ phase B: gather
-    GatherCtx g{sF, sIdx, sXv, sE, F, K, num, C, EP, nrows, tid, nthreads};
-    if (!any_qr) { if (vec2) issue_rows<2, FT, KT, true>(g); else issue_rows<1, FT, KT, true>(g); }
-    else         { if (vec2) issue_rows<2, FT, KT, false>(g); else issue_rows<1, FT, KT, false>(g); }
-    // rows of samples past the end of the batch: zeros (never written out, keeps phase D finite)
-#pragma unroll 1
-    for (uint32_t e = tid; e < (uint32_t)((kS - nrows) * FK); e += nthreads) {
-        const uint32_t s = e / (uint32_t)FK;
-        sE[(nrows + s) * EP + (e - s * FK)] = 0.f;
-    }
-
-    // first-order table values of this thread's fields f = kk, kk+K, ...   (model/DeepFMs.py:300-309)
-    float first_acc = 0.f;
-    const bool owner = kk < K;
-    const bool live_sample = smp < nrows;
-    if (!fwlw && live_sample && owner) {
-#pragma unroll 4
-        for (int f = kk; f < F; f += K) {
-            const dfw_field_desc& fd = sF[f];
-            const int32_t idx = f < num ? 0 : sIdx[smp * C + (f - num)];
-            float v;
-            if (fd.qr1_op != DFW_TABLE_PLAIN) {
-                const uint32_t c = (uint32_t)fd.collisions;
-                const uint32_t q = (uint32_t)idx / c, r = (uint32_t)idx - q * c;
-                const float a = __ldg(fd.w1 + q), b = __ldg(fd.w1_r + r);
-                v = fd.qr1_op == DFW_TABLE_QR_MULT ? a * b : a + b;
-            } else {
-                v = __ldg(fd.w1 + idx);
-            }
-            if (f < num) v *= sXv[smp * num + f];
-            if (p.flags & DFW_USE_LW) v *= __ldg(p.fm1 + f);                              // model/DeepFMs.py:450
-            first_acc += v;
-        }
-    }
-
-    DFW_CLK(3);
-    cp_async_wait_all();
-    if (any_qr || num > 0) {
-        __syncthreads();   // every thread's pieces have landed: fix rows up in place
-        fixup_rows<FT, KT>(g, any_qr);
-    }
-    __syncthreads();   // E block complete
-    DFW_CLK(4);
+    float first_acc[1];
+    embed_gather<FT, KT, kS, 1, 0>(p, sm, smem_raw + L.oImg, true, tid, nthreads, b0, nrows, first_acc, clk);
 
     // ------------------------------------------------------------------ phase C: stream E out
     if (p.E) {
@@ -444,77 +189,7 @@ embed_fwfm_kernel(const EmbedParams p) {
         }
     }
 
-    DFW_CLK(5);
-    // ------------------------------------------------------------------ phase D: first + second order
-    if (owner) {
-        const float* myE = sE + smp * EP + kk;   // E[s][f][k] at myE[f*K]
-        float acc = first_acc;
-        if (fwlw) {                                // model/DeepFMs.py:344-345
-            float a0 = 0.f, a1 = 0.f;
-            int f = 0;
-#pragma unroll 2
-            for (; f + 1 < F; f += 2) {
-                a0 = fmaf(myE[f * K], sWl[f * K + kk], a0);
-                a1 = fmaf(myE[(f + 1) * K], sWl[(f + 1) * K + kk], a1);
-            }
-            if (f < F) a0 = fmaf(myE[f * K], sWl[f * K + kk], a0);
-            acc = a0 + a1;
-        }
-        float second = 0.f;
-        if (use_list) {
-            const int n = hdr->n_list;
-            float s0 = 0.f, s1 = 0.f;
-            int q = 0;
-#pragma unroll 1
-            for (; q + 1 < n; q += 2) {
-                const PairEnt a = sPairs[q], b = sPairs[q + 1];
-                s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
-                s1 = fmaf(b.u * myE[b.ij & 0xffffu], myE[b.ij >> 16], s1);
-            }
-            if (q < n) {
-                const PairEnt a = sPairs[q];
-                s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
-            }
-            second = s0 + s1;
-        } else if constexpr (FT > 0) {
-            constexpr int FTc = FT > 0 ? FT : 2, KTc = KT > 0 ? KT : 1;
-            float e[FTc], t[FTc];
-#pragma unroll
-            for (int f = 0; f < FTc; ++f) { e[f] = myE[f * KTc]; t[f] = 0.f; }
-            const float4* sU4 = reinterpret_cast<const float4*>(sU);
-#pragma unroll
-            for (int j = 1; j < FTc; ++j) {
-                const int off4 = ucol_off(j) >> 2;
-#pragma unroll
-                for (int c4 = 0; c4 < pad4(j) / 4; ++c4) {
-                    const float4 u = sU4[off4 + c4];
-                    const int i = 4 * c4;
-                    if (i + 0 < j) t[i + 0] = fmaf(u.x, e[j], t[i + 0]);
-                    if (i + 1 < j) t[i + 1 < FTc ? i + 1 : 0] = fmaf(u.y, e[j], t[i + 1 < FTc ? i + 1 : 0]);
-                    if (i + 2 < j) t[i + 2 < FTc ? i + 2 : 0] = fmaf(u.z, e[j], t[i + 2 < FTc ? i + 2 : 0]);
-                    if (i + 3 < j) t[i + 3 < FTc ? i + 3 : 0] = fmaf(u.w, e[j], t[i + 3 < FTc ? i + 3 : 0]);
-                }
-            }
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int i = 0; i + 1 < FTc; i += 2) {
-                s0 = fmaf(e[i], t[i], s0);
-                if (i + 1 < FTc - 1) s1 = fmaf(e[i + 1], t[i + 1], s1);
-            }
-            second = s0 + s1;
-        }
-        sPart[kk * kS + smp] = acc + second;
-    }
-    __syncthreads();
-
-    DFW_CLK(6);
-    // ------------------------------------------------------------------ phase E: reduce over k
-    if (tid < nrows) {
-        float tot = 0.f;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) tot += sPart[k * kS + tid];
-        p.shallow[b0 + tid] = tot + __ldg(p.bias);
-    }
+    embed_interact<FT, KT, kS, 1, 0>(p, sm, tid, nthreads, nrows, first_acc, p.shallow + b0, clk);
 }
 
 template <int FT, int KT>

@@ -1,0 +1,595 @@
+// The whole DeepFwFM forward of a 32-sample tile in ONE kernel: gather + Xv scale + first order + FwFM second order on
+// the CUDA cores, the deep MLP on tcgen05 tensor cores (TMA-fed weights, TMEM accumulators), fused logit / sigmoid.
+//
+// Replaces the body of DeepFMs.forward (model/DeepFMs.py:285-469) and the sigmoid of :777.
+//
+// Why "transposed": at the reference's batch sizes (B = 4096) a sample-major GEMM tile (128 samples x N) gives only 32
+// CTAs for 148 SMs.  Here the OUTPUT NEURONS are the MMA's M dimension (128 rows of W_l per tile = one TMA box of
+// nn.Linear's (out, in) layout, K-major as stored) and the SAMPLES are N = 32, so a CTA owns 32 samples, B = 4096 is
+// 128 CTAs, and activations never leave the SM:  D_l^T (neurons x samples, TMEM) = W_l (smem, streamed) x X_l^T (smem).
+//
+//   CTA = 512 threads, one per SM, cluster of `cluster` CTAs sharing every weight box by TMA multicast:
+//     warp 0      TMA producer: streams (layer, 128-neuron tile, 64-wide K chunk) weight boxes through an mbarrier ring;
+//                 each CTA of the cluster fetches 1/cluster of the box's rows and multicasts it to all
+//     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128 (64 for a short last tile), N = 32 / 64, K = 16
+//     warps 2-5   epilogue: thread = one neuron (TMEM lane); tcgen05.ld its 32 samples, + bias, ReLU, -> bf16 into the
+//                 next layer's operand buffer (K-major, 128B swizzle); last layer: dot with net_1_fc in registers,
+//                 warp-transpose reduction, + shallow, optional sigmoid -> global
+//     warps 6-15  gather group (embed_device.cuh): indices -> rows (cp.async) -> fix-ups -> bf16 operand of layer 1,
+//                 then first order + FwFM second order in fp32 while the tensor cores already run layer 1
+//
+//   SPLIT = false ("bf16"):   operands rounded to bf16, fp32 accumulate -- the looser-bound path (5e-4 * max|logit|)
+//   SPLIT = true  ("bf16x3"): every fp32 operand is split x = hi + lo (two bf16), and the product is
+//                 W_hi X_hi + W_hi X_lo + W_lo X_hi with fp32 accumulation: relative error ~2^-17 per product, which
+//                 keeps the logits inside the reference's fp32 bound (1e-5 * max|logit|; measured 2e-7..2e-6 on the
+//                 golden cases).  X_hi and X_lo are stacked along N (one N = 64 MMA against W_hi), W_lo X_hi is a second
+//                 N = 32 MMA into the same accumulator columns: 2x the tensor time of bf16, not 3x.
+//
+//   Shared memory: X0 | X1 (activation ping-pong; the fp32 gather block aliases X1) | weight ring | shallow image | misc
+//   TMEM: 2 x 256 columns (layer parity) x (<= 4 neuron tiles x 32|64 sample columns)
+//   Limits of the fused form: depth <= 4, widths <= 512, F*K <= 512, K <= 20.  Other shapes take the staged path.
+#include <stdlib.h>
+
+#include "embed_device.cuh"
+#include "tc_common.cuh"
+
+namespace dfw {
+namespace fz {
+
+using namespace dfw::tc;
+
+constexpr int TS = 32;                         // samples per tile
+constexpr int G_WARPS = 10;
+constexpr int G_THREADS = 32 * G_WARPS;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int NTHREADS = 64 + EPI_THREADS + G_THREADS;     // 512
+constexpr int STAGE_BYTES = 128 * 128;         // one weight box: 128 neurons x 64 bf16
+constexpr int MAX_STAGES = 12;
+constexpr int MAX_L = 4;
+constexpr int MAX_MT = 4;                      // 128-neuron tiles per layer (width <= 512)
+constexpr int MAX_W = 512;
+constexpr int G_ROUNDS = 2;                    // phase-D rounds of the gather group: K <= G_ROUNDS * G_WARPS
+constexpr int BAR_GATHER = 1, BAR_EPI = 2;     // named barriers
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+struct alignas(64) Maps {
+    CUtensorMap w[MAX_L][2][2];                // [layer][hi | lo][128-row tile | 64-row last tile]
+};
+
+struct Params {
+    EmbedParams ep;
+    int depth, in_dim;
+    int widths[MAX_L];
+    const float* bias[MAX_L];
+    const float* fc;
+    float* logits;
+    float* prob;
+    long long B;
+    int num_tiles, cluster;
+    int x_chunks;                               // 64-wide K chunks per activation buffer
+    int nstage;
+    uint32_t oX1, oRing, oImg, oPart, oIdx, oXv, oMisc;   // shared-memory offsets from the 1024-aligned base
+    int* err;
+    long long* clk;                             // optional per-CTA timeline (debug tooling): 32 x int64 per CTA
+};
+#define FZ_CLK(slot) do { if (p.clk) p.clk[blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+// neuron tiles of a layer of (padded) width npad: 128 rows each; a last tile of <= 16 rows runs as M = 64
+__host__ __device__ inline int n_mtiles(int npad) { return (npad + 127) / 128; }
+__host__ __device__ inline int mtile_rows(int npad, int mt) {
+    const int rem = npad - mt * 128;
+    return rem >= 128 ? 128 : (rem <= 16 ? 64 : 128);
+}
+
+struct Bars {
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    uint64_t x_ready, shallow_ready, tile_done;
+    uint64_t act_ready[2][MAX_MT], acc_full[2][MAX_MT];
+    uint32_t tmem_holder, pad_;
+    float shallow[TS];
+    float red[EPI_WARPS][TS];
+};
+
+// ---------------------------------------------------------------------------------------- the kernel
+template <bool SPLIT, int FT, int KT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fused_forward_kernel(const __grid_constant__ Maps maps, const Params p) {
+    constexpr int NB = SPLIT ? 64 : 32;                 // B-operand rows per chunk == accumulator columns per neuron tile
+    constexpr int CH = NB * 128;                        // bytes of one 64-wide K chunk of an activation buffer
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment: the 128B swizzle is a function of shared-memory address bits [4,10)
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sX[2] = {base, base + p.oX1};
+    unsigned char* sW = base + p.oRing;
+    Bars* bars = reinterpret_cast<Bars*>(base + p.oMisc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.depth, NSTAGE = p.nstage, CL = p.cluster;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL); }
+        mbar_init(&bars->x_ready, G_THREADS);
+        mbar_init(&bars->shallow_ready, G_THREADS);
+        mbar_init(&bars->tile_done, EPI_THREADS);
+        for (int b = 0; b < 2; ++b)
+            for (int m = 0; m < MAX_MT; ++m) { mbar_init(&bars->act_ready[b][m], EPI_THREADS); mbar_init(&bars->acc_full[b][m], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int l = 0; l < L; ++l)
+            for (int h = 0; h < (SPLIT ? 2 : 1); ++h) { tma_prefetch_desc(&maps.w[l][h][0]); tma_prefetch_desc(&maps.w[l][h][1]); }
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_holder, 512);
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();    // the peers' barriers exist before anything is multicast to them
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_holder;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    // every CTA of a cluster runs the same number of tiles (the weight ring is shared); tiles past the end are dummies
+    const int n_iter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
+    auto layer_n = [&](int l) { return pad16(p.widths[l]); };
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one lane)
+        if (lane == 0) {
+            int stage = 0; uint32_t sphase = 0;
+            for (int it = 0; it < n_iter; ++it) {
+                for (int l = 0; l < L; ++l) {
+                    const int kch = (layer_k(l) + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int rows = mtile_rows(npad, mt), per = rows / CL;
+                        for (int c = 0; c < kch; ++c) {
+#pragma unroll
+                            for (int h = 0; h < (SPLIT ? 2 : 1); ++h) {
+                                mbar_wait(&bars->empty[stage], sphase ^ 1, p.err, 12);
+                                mbar_expect_tx(&bars->full[stage], (uint32_t)(rows * 128));
+                                unsigned char* dst = sW + (size_t)stage * STAGE_BYTES + (size_t)crank * per * 128;
+                                const CUtensorMap* map = &maps.w[l][h][rows == 64 ? 1 : 0];
+                                if (CL > 1) tma_load_2d_mc(dst, map, &bars->full[stage], c * KCH, mt * 128 + (int)crank * per, cmask);
+                                else tma_load_2d(dst, map, &bars->full[stage], c * KCH, mt * 128);
+                                if (++stage == NSTAGE) { stage = 0; sphase ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one lane)
+        if (lane == 0) {
+            int stage = 0; uint32_t sphase = 0;
+            uint32_t act_cnt[2][MAX_MT] = {};
+            for (int it = 0; it < n_iter; ++it) {
+                if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 20);   // TMEM drained, X buffers free
+                for (int l = 0; l < L; ++l) {
+                    const int buf = l & 1;
+                    const int K = layer_k(l), kch = (K + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int rows = mtile_rows(npad, mt);
+                        const uint32_t idesc = make_idesc(rows, NB), idesc_lo = make_idesc(rows, 32);
+                        const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + mt * NB);
+                        for (int c = 0; c < kch; ++c) {
+                            if (mt == 0) {
+                                if (l == 0) {
+                                    if (c == 0) { if (it == 0) FZ_CLK(0); mbar_wait(&bars->x_ready, (uint32_t)(it & 1), p.err, 21); if (it == 0) FZ_CLK(1); }
+                                } else if ((c & 1) == 0) {
+                                    // chunk c holds neurons [64c, 64c+64) of the previous layer = its neuron tile c/2
+                                    const int g = c >> 1;
+                                    mbar_wait(&bars->act_ready[buf][g], act_cnt[buf][g] & 1, p.err, 22);
+                                    ++act_cnt[buf][g];
+                                }
+                            }
+                            const int ksteps = min(4, (K - c * KCH) / 16);
+                            const uint64_t bdesc0 = make_desc_sw128(smem_u32(sX[buf] + (size_t)c * CH));
+#pragma unroll
+                            for (int h = 0; h < (SPLIT ? 2 : 1); ++h) {
+                                mbar_wait(&bars->full[stage], sphase, p.err, 24);
+                                tc_fence_after();
+                                const uint64_t adesc0 = make_desc_sw128(smem_u32(sW + (size_t)stage * STAGE_BYTES));
+                                for (int ks = 0; ks < ksteps; ++ks)      // +32 bytes (16 bf16) along K inside the swizzle atom
+                                    umma_bf16(dcol, adesc0 + (uint64_t)(ks * 2), bdesc0 + (uint64_t)(ks * 2), h ? idesc_lo : idesc,
+                                              (h | c | ks) ? 1u : 0u);
+                                if (CL > 1) umma_commit_mc(&bars->empty[stage], cmask);   // this CTA is done with the stage (all CTAs are told)
+                                else umma_commit(&bars->empty[stage]);
+                                if (++stage == NSTAGE) { stage = 0; sphase ^= 1; }
+                            }
+                        }
+                        umma_commit(&bars->acc_full[buf][mt]);          // accumulators of (layer l, neuron tile mt) complete
+                        if (it == 0 && l < 4 && mt == MT - 1) FZ_CLK(2 + l);
+                    }
+                }
+            }
+        }
+    } else if (warp < 2 + EPI_WARPS) {
+        // ================================================================= epilogue warps (thread = neuron)
+        const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q4 * 32 + lane;
+        const int ewarp = warp - 2;
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        uint32_t acc_cnt[2][MAX_MT] = {};
+        for (int it = 0; it < n_iter; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            float part[TS];
+#pragma unroll
+            for (int s = 0; s < TS; ++s) part[s] = 0.f;
+            for (int l = 0; l < L; ++l) {
+                const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad);
+                const bool last = (l == L - 1);
+                unsigned char* xn = sX[(l + 1) & 1];
+                for (int mt = 0; mt < MT; ++mt) {
+                    mbar_wait(&bars->acc_full[buf][mt], acc_cnt[buf][mt] & 1, p.err, 31);
+                    ++acc_cnt[buf][mt];
+                    if (threadIdx.x == 64 && it == 0 && l < 4 && mt == 0) FZ_CLK(8 + 2 * l);
+                    tc_fence_after();
+                    const int n = mt * 128 + row;
+                    const int rows_valid = min(128, npad - mt * 128);   // neurons [N, npad) are zero rows: they write the K padding
+                    if (q4 * 32 < rows_valid) {                     // warp-uniform: some lane of this quarter holds a neuron
+                        uint32_t d[32];
+                        tmem_ld32(taddr_row + (uint32_t)(buf * 256 + mt * NB), d);
+                        float v[32];
+                        if constexpr (SPLIT) {
+                            uint32_t d2[32];
+                            tmem_ld32(taddr_row + (uint32_t)(buf * 256 + mt * NB + 32), d2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int s = 0; s < TS; ++s) v[s] = __uint_as_float(d[s]) + __uint_as_float(d2[s]);
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int s = 0; s < TS; ++s) v[s] = __uint_as_float(d[s]);
+                        }
+                        if (row < rows_valid) {
+                            const float bb = n < N ? __ldg(p.bias[l] + n) : 0.f;
+                            if (last) {
+                                const float ff = n < N ? __ldg(p.fc + n) : 0.f;
+#pragma unroll
+                                for (int s = 0; s < TS; ++s) part[s] = fmaf(fmaxf(v[s] + bb, 0.f), ff, part[s]);
+                            } else {
+                                // element (sample s, k = n) of the next operand: chunk n/64, row s (hi) / 32+s (lo), 16-byte unit
+                                // ((n%64)/8) ^ (row%8), byte (n%8)*2
+                                unsigned char* xc = xn + (size_t)(n >> 6) * CH + (n & 7) * 2;
+                                const int u = (n & 63) >> 3;
+#pragma unroll
+                                for (int s = 0; s < TS; ++s) {
+                                    const float a = fmaxf(v[s] + bb, 0.f);
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+                                    unsigned char* dst = xc + s * 128 + ((u ^ (s & 7)) << 4);
+                                    *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                                    if constexpr (SPLIT)
+                                        *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(a - __bfloat162float(hi));
+                                }
+                            }
+                        }
+                    }
+                    if (!last) {
+                        fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
+                        tc_fence_before();             // TMEM reads ordered before the arrive
+                        mbar_arrive(&bars->act_ready[(l + 1) & 1][mt]);
+                    }
+                    if (threadIdx.x == 64 && it == 0 && l < 4 && mt == MT - 1) FZ_CLK(9 + 2 * l);
+                }
+            }
+            // per-sample sum over this warp's neurons: transpose-reduce 32 values x 32 lanes -> lane s holds sample s
+#pragma unroll
+            for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < nn / 2; ++i) {
+                    const float send = up ? part[i] : part[i + nn / 2];
+                    const float keep = up ? part[i + nn / 2] : part[i];
+                    part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            bars->red[ewarp][lane] = part[0];
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_EPI), "n"(EPI_THREADS) : "memory");
+            if (ewarp == 0) {
+                mbar_wait(&bars->shallow_ready, (uint32_t)(it & 1), p.err, 33);
+                const long long b = (long long)tile * TS + lane;
+                float z = bars->shallow[lane];
+#pragma unroll
+                for (int w = 0; w < EPI_WARPS; ++w) z += bars->red[w][lane];
+                if (b < p.B) {
+                    if (p.logits) p.logits[b] = z;
+                    if (p.prob) p.prob[b] = 1.0f / (1.0f + expf(-z));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->tile_done);
+            if (threadIdx.x == 64 && it == 0) FZ_CLK(16);
+        }
+    } else {
+        // ================================================================= gather group
+        const int gtid = threadIdx.x - (64 + EPI_THREADS);
+        const int F = FT > 0 ? FT : p.ep.F, K = KT > 0 ? KT : p.ep.K;
+        const int FK = F * K;
+        TileSmem sm;
+        sm.img = base + p.oImg;
+        sm.E = reinterpret_cast<float*>(sX[1]);         // the fp32 block aliases X1 (free until layer 1's epilogue)
+        sm.part = reinterpret_cast<float*>(base + p.oPart);
+        sm.idx = reinterpret_cast<int32_t*>(base + p.oIdx);
+        sm.xv = reinterpret_cast<float*>(base + p.oXv);
+        sm.EP = e_pitch(FK);
+        const int units = pad16(FK) >> 3;               // 16-byte (8 x bf16) units per operand row
+        for (int it = 0; it < n_iter; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int64_t b0 = (int64_t)tile * TS;
+            int64_t left = p.ep.B - b0;
+            const int nrows = (int)(left < 0 ? 0 : (left > TS ? TS : left));
+            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 40);      // X1 (= the fp32 block) is free again
+            float first_acc[G_ROUNDS];
+            embed_gather<FT, KT, TS, G_ROUNDS, BAR_GATHER>(p.ep, sm, base + p.oImg, it == 0, gtid, G_THREADS, b0, nrows, first_acc, nullptr);
+            if (gtid == 0 && it == 0) FZ_CLK(20);
+            // fp32 block -> bf16 (hi | lo) operand of layer 1: X0[s][k], K-major, 128B swizzle; columns >= F*K are zero
+            for (int i = gtid; i < TS * units; i += G_THREADS) {
+                const int s = i / units, u8 = i - s * units;
+                const float* src = sm.E + s * sm.EP + 8 * u8;
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c0 = 8 * u8 + 2 * j;
+                    float2 t = make_float2(0.f, 0.f);
+                    if (c0 + 1 < FK) t = *reinterpret_cast<const float2*>(src + 2 * j);
+                    else if (c0 < FK) t.x = src[2 * j];
+                    x[2 * j] = t.x; x[2 * j + 1] = t.y;
+                }
+                uint4 hi4, lo4;
+                uint32_t* hp = reinterpret_cast<uint32_t*>(&hi4);
+                uint32_t* lp = reinterpret_cast<uint32_t*>(&lo4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                    hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                    if constexpr (SPLIT) {
+                        const float2 hf = __bfloat1622float2(h2);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+                        lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                }
+                unsigned char* dst = sX[0] + (size_t)(u8 >> 3) * CH + s * 128 + (((u8 & 7) ^ (s & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = hi4;
+                if constexpr (SPLIT) *reinterpret_cast<uint4*>(dst + 32 * 128) = lo4;
+            }
+            fence_async_smem();
+            mbar_arrive(&bars->x_ready);
+            if (gtid == 0 && it == 0) FZ_CLK(21);
+            embed_interact<FT, KT, TS, G_ROUNDS, BAR_GATHER>(p.ep, sm, gtid, G_THREADS, nrows, first_acc, bars->shallow, nullptr);
+            mbar_arrive(&bars->shallow_ready);
+            if (gtid == 0 && it == 0) FZ_CLK(22);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();    // no CTA exits while a peer may still multicast into it
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// fp32 (out, in) row-major -> bf16 hi (and lo = bf16(w - hi)) images (pad16(out), pad64(in)), zero padded
+__global__ void pack_split_kernel(const float* __restrict__ W, int out_dim, int in_dim, int out_pad, int in_pad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long total = (long long)out_pad * in_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / in_pad), c = (int)(i - (long long)r * in_pad);
+        const float w = (r < out_dim && c < in_dim) ? W[(long long)r * in_dim + c] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        if (hi) hi[i] = h;
+        if (lo) lo[i] = __float2bfloat16_rn(w - __bfloat162float(h));
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static long long* g_clk = nullptr;
+
+struct Plan {
+    Params p;
+    size_t smem_bytes;
+};
+
+// Shared-memory plan; returns false (with `why`) when the shapes do not fit the fused form.
+static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why) {
+    const int F = m->field_size, K = m->embedding_size, num = m->numerical, FK = F * K;
+    *why = nullptr;
+    if (!(m->flags & DFW_USE_DEEP)) { *why = "no deep part"; return false; }
+    if (m->depth > MAX_L) { *why = "depth > 4"; return false; }
+    if (FK > MAX_W) { *why = "F*K > 512"; return false; }
+    if (K > G_ROUNDS * G_WARPS) { *why = "K > 20"; return false; }
+    int kmax = pad16(FK);
+    for (int l = 0; l < m->depth; ++l) {
+        if (m->widths[l] > MAX_W) { *why = "layer width > 512"; return false; }
+        if (!m->Wbf16[l] || (split && !m->Wbf16_lo[l])) { *why = "bf16 weight image missing"; return false; }
+        if (l + 1 < m->depth && pad16(m->widths[l]) > kmax) kmax = pad16(m->widths[l]);
+    }
+    Params& p = pl.p;
+    const int NB = split ? 64 : 32, CH = NB * 128;
+    p.x_chunks = (kmax + KCH - 1) / KCH;
+    const TileSizes ts = tile_sizes(F, K, num, TS);
+    size_t x0 = (size_t)p.x_chunks * CH;
+    size_t x1 = x0 > ts.bE ? x0 : ts.bE;
+    x1 = (x1 + 1023) / 1024 * 1024;
+    size_t o = 0;
+    o += x0;                       p.oX1 = (uint32_t)o;
+    o += x1;                       p.oRing = (uint32_t)o;
+    const size_t tail = up16(img_layout(F, K).total) + ts.bPart + ts.bIdx + ts.bXv + up16(sizeof(Bars)) + 64;
+    if (o + tail + 1024 + 4 * (size_t)STAGE_BYTES > SMEM_LIMIT) { *why = "shared memory: fewer than 4 weight stages fit"; return false; }
+    int nstage = (int)((SMEM_LIMIT - 1024 - o - tail) / STAGE_BYTES);
+    if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+    p.nstage = nstage;
+    o += (size_t)nstage * STAGE_BYTES;   p.oImg = (uint32_t)o;
+    o += up16(img_layout(F, K).total);   p.oPart = (uint32_t)o;
+    o += ts.bPart;                       p.oIdx = (uint32_t)o;
+    o += ts.bIdx;                        p.oXv = (uint32_t)o;
+    o += ts.bXv;                         p.oMisc = (uint32_t)((o + 15) & ~size_t(15));
+    o = p.oMisc + sizeof(Bars);
+    pl.smem_bytes = o + 1024;
+    return true;
+}
+
+template <bool SPLIT, int FT, int KT>
+static int launch(const Maps& maps, const Plan& pl, int grid, cudaStream_t st) {
+    auto kern = fused_forward_kernel<SPLIT, FT, KT>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DFW_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, maps, pl.p));
+    count_launch();
+    return check_launch("fused_forward_kernel");
+}
+
+// how many clusters of `cl` CTAs of this kernel the device can hold at once (cached per device and cluster size)
+template <bool SPLIT, int FT, int KT>
+static int max_clusters(int cl, size_t smem_bytes) {
+    static thread_local int cache[8][5] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && cache[dev][cl] > 0) return cache[dev][cl];
+    auto kern = fused_forward_kernel<SPLIT, FT, KT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cl * 64));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n <= 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = sms / cl * 7 / 8;
+    }
+    if (dev < 8) cache[dev][cl] = n;
+    return n;
+}
+
+template <bool SPLIT, int FT, int KT>
+static int run(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st) {
+    Params& p = pl.p;
+    // cluster size: the largest of {4, 2, 1} that still covers all tiles in the fewest waves
+    int best_cl = 1, best_grid = 1, best_iter = 1 << 30;
+    for (int cl = 4; cl >= 1; cl >>= 1) {
+        const int mc = cl == 1 ? 148 : max_clusters<SPLIT, FT, KT>(cl, pl.smem_bytes);
+        if (mc <= 0) continue;
+        const int need = (p.num_tiles + cl - 1) / cl;
+        const int clusters = need < mc ? need : mc;
+        const int grid = clusters * cl;
+        const int iters = (p.num_tiles + grid - 1) / grid;
+        if (iters < best_iter) { best_iter = iters; best_cl = cl; best_grid = grid; }
+    }
+    if (const char* e = getenv("DFW_FUSED_CLUSTER")) {
+        const int cl = atoi(e);
+        if (cl == 1 || cl == 2 || cl == 4) {
+            const int mc = cl == 1 ? 148 : max_clusters<SPLIT, FT, KT>(cl, pl.smem_bytes);
+            const int need = (p.num_tiles + cl - 1) / cl;
+            best_cl = cl; best_grid = (need < mc ? need : mc) * cl;
+        }
+    }
+    p.cluster = best_cl;
+    int k = p.in_dim;
+    for (int l = 0; l < m->depth; ++l) {
+        const int npad = pad16(m->widths[l]), kpad = (k + 63) / 64 * 64;
+        for (int h = 0; h < (SPLIT ? 2 : 1); ++h) {
+            const void* img = h ? m->Wbf16_lo[l] : m->Wbf16[l];
+            if (int rc = make_map(&maps.w[l][h][0], img, npad, kpad, kpad, 128 / best_cl)) return rc;
+            if (int rc = make_map(&maps.w[l][h][1], img, npad, kpad, kpad, 64 / best_cl)) return rc;
+        }
+        k = m->widths[l];
+    }
+    return launch<SPLIT, FT, KT>(maps, pl, best_grid, st);
+}
+
+}  // namespace fz
+}  // namespace dfw
+
+using namespace dfw;
+
+// Debug tooling (not part of the product ABI): per-CTA clock64() timeline of the next fused launches.
+extern "C" void dfw_debug_set_fused_clock_buffer(void* dev_buf) { fz::g_clk = static_cast<long long*>(dev_buf); }
+
+extern "C" int dfw_fused_supported(const dfw_model* m, int precision) {
+    if (check_model(m)) return 0;
+    if (precision != DFW_PREC_BF16 && precision != DFW_PREC_BF16X3) return 0;
+    fz::Plan pl;
+    const char* why;
+    return fz::make_plan(m, precision == DFW_PREC_BF16X3, pl, &why) ? 1 : 0;
+}
+
+extern "C" int dfw_pack_mlp_bf16_split(const float* W, int32_t out_dim, int32_t in_dim, void* dst_hi, void* dst_lo, void* stream) {
+    DFW_REQUIRE(W && (dst_hi || dst_lo) && out_dim > 0 && in_dim > 0, DFW_E_ARG, "bad pack_mlp_bf16_split arguments");
+    const int out_pad = tc::pad16(out_dim), in_pad = (in_dim + 63) / 64 * 64;
+    fz::pack_split_kernel<<<148, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        W, out_dim, in_dim, out_pad, in_pad, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo));
+    count_launch();
+    return check_launch("pack_split_kernel");
+}
+
+extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
+                                 const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
+                                 float* logits_out, float* prob_out, int32_t* err_word, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    DFW_REQUIRE(precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3, DFW_E_ARG,
+                "the fused kernel computes in bf16 or bf16x3, not precision %d", precision);
+    DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");
+    if (B == 0) return 0;
+    DFW_REQUIRE(logits_out || prob_out, DFW_E_ARG, "no output requested");
+    DFW_REQUIRE(m->shallow_image, DFW_E_ARG, "model has no shallow image (call dfw_pack_shallow)");
+    const int F = m->field_size, K = m->embedding_size, num = m->numerical;
+    DFW_REQUIRE(F - num == 0 || xi, DFW_E_ARG, "xi is NULL");
+    DFW_REQUIRE(num == 0 || xv, DFW_E_ARG, "xv is NULL");
+    const bool split = precision == DFW_PREC_BF16X3;
+    fz::Plan pl;
+    const char* why = nullptr;
+    DFW_REQUIRE(fz::make_plan(m, split, pl, &why), DFW_E_UNSUPPORTED, "fused forward: %s", why ? why : "unsupported shape");
+    fz::Params& p = pl.p;
+    EmbedParams& e = p.ep;
+    e.image = static_cast<const unsigned char*>(m->shallow_image);
+    e.xi = xi; e.xi_sb = xi_stride_b; e.xi_sc = xi_stride_c;
+    e.xv = xv; e.xv_sb = xv_stride_b; e.xv_sc = xv_stride_c;
+    e.fm1 = m->fm_1st; e.bias = m->bias;
+    e.E = nullptr; e.ldE = 0; e.Eb = nullptr; e.ldEb = 0; e.shallow = nullptr;
+    e.err = (m->flags & DFW_CHECK_INDEX) ? err_word : nullptr;
+    e.B = B; e.F = F; e.num = num; e.K = K; e.flags = m->flags; e.clk = nullptr;
+    p.depth = m->depth; p.in_dim = F * K;
+    for (int l = 0; l < m->depth; ++l) { p.widths[l] = m->widths[l]; p.bias[l] = m->b[l]; }
+    p.fc = m->fc; p.logits = logits_out; p.prob = prob_out; p.B = B;
+    p.num_tiles = (int)((B + fz::TS - 1) / fz::TS);
+    p.err = err_word; p.clk = fz::g_clk;
+    fz::Maps maps;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the two dataset shapes BASELINE.json names get the fully unrolled dense second order
+    if (split) {
+        if (F == 39 && K == 10) return fz::run<true, 39, 10>(m, pl, maps, st);
+        if (F == 47 && K == 10) return fz::run<true, 47, 10>(m, pl, maps, st);
+        return fz::run<true, 0, 0>(m, pl, maps, st);
+    }
+    if (F == 39 && K == 10) return fz::run<false, 39, 10>(m, pl, maps, st);
+    if (F == 47 && K == 10) return fz::run<false, 47, 10>(m, pl, maps, st);
+    return fz::run<false, 0, 0>(m, pl, maps, st);
+}

@@ -170,13 +170,23 @@ class _Plan:
         for l in range(owner.h_depth):
             lin = getattr(owner, f"net_1_linear_{l + 1}")
             out_dim = lin.out_features
-            if precision == "bf16":
+            if precision in ("bf16", "bf16x3"):
+                # hi = bf16(W); bf16x3 adds lo = bf16(W - hi) (split operands, see csrc/fused_tc.cu)
                 nbytes = lib.dfw_pack_mlp_bf16_bytes(out_dim, in_dim)
-                img = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-                _lib.check(lib.dfw_pack_mlp_bf16(lin.weight.data_ptr(), out_dim, in_dim, img.data_ptr(), st),
-                           "dfw_pack_mlp_bf16")
-                m.Wbf16[l] = img.data_ptr()
-                self.keep.append(img)
+                hi = lo = None
+                if not m.Wbf16[l]:
+                    hi = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if precision == "bf16x3":
+                    lo = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if hi is not None or lo is not None:
+                    _lib.check(lib.dfw_pack_mlp_bf16_split(lin.weight.data_ptr(), out_dim, in_dim, _ptr(hi), _ptr(lo), st),
+                               "dfw_pack_mlp_bf16_split")
+                if hi is not None:
+                    m.Wbf16[l] = hi.data_ptr()
+                    self.keep.append(hi)
+                if lo is not None:
+                    m.Wbf16_lo[l] = lo.data_ptr()
+                    self.keep.append(lo)
             else:  # fp32_csr
                 row_ptr = torch.empty(out_dim + 1, dtype=torch.int32, device=self.device)
                 _lib.check(lib.dfw_csr_count(lin.weight.data_ptr(), out_dim, in_dim, row_ptr.data_ptr(), st),

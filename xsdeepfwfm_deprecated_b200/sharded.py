@@ -222,6 +222,7 @@ class ShardedDeepFMs(DeepFMs):
         plan.ensure_image(self, self.precision)
         for l in range(self.h_depth if self.use_deep else 0):
             m.Wbf16[l] = plan.model.Wbf16[l]
+            m.Wbf16_lo[l] = plan.model.Wbf16_lo[l]
             m.csr[l] = plan.model.csr[l]
         ref = C.byref(m)
         nbytes = lib.dfw_forward_workspace_bytes(ref, B, prec)
