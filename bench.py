@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--precision", default=os.environ.get("DFW_BENCH_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("DFW_BENCH_PRECISION", "bf16x3"),
+                    choices=["bf16x3", "bf16", "fp32", "fp32_csr"])
     ap.add_argument("--nbatches", type=int, default=256, help="distinct input batches cycled (> L2 in total)")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -234,32 +235,7 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- per-stage timing for the roofline (live, CUDA events, same stream, same inputs) -------------
-    FK = FIELD * K_EMB
-    ldE, ldEb = (FK + 3) // 4 * 4, (FK + 7) // 8 * 8
-    Bp = (B + 127) // 128 * 128
-    E = torch.zeros(Bp, ldE, device=device)
-    Eb = torch.zeros(Bp, ldEb, device=device, dtype=torch.bfloat16)
-    shallow = torch.zeros(Bp, device=device)
-    mws = torch.zeros(lib.dfw_mlp_workspace_bytes(plan.model_ref, B, prec) + 4096, dtype=torch.uint8, device=device)
-    bf = args.precision == "bf16"
-
-    def embed(i):
-        j = i % nb
-        rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B,
-                                None if bf else E.data_ptr(), ldE, Eb.data_ptr() if bf else None, ldEb,
-                                shallow.data_ptr(), None, sp)
-        if rc:
-            _lib.check(rc, "dfw_embed_fwfm")
-
-    mlp_fn = {"fp32": lib.dfw_mlp_fp32, "fp32_csr": lib.dfw_mlp_csr, "bf16": lib.dfw_mlp_bf16}[args.precision]
-
-    def mlp(i):
-        rc = mlp_fn(plan.model_ref, Eb.data_ptr() if bf else E.data_ptr(), ldEb if bf else ldE, B, shallow.data_ptr(),
-                    mws.data_ptr(), mws.numel(), logits[i % nb].data_ptr(), None, sp)
-        if rc:
-            _lib.check(rc, "dfw_mlp")
-
+    # ---- per-kernel timing for the roofline (live, CUDA events, same stream, same inputs) -------------
     def graph_time(fn, n_it):
         """ms per call of `fn`, replayed from a CUDA graph of n_it calls over distinct batches (device time only)."""
         g = torch.cuda.CUDAGraph()
@@ -271,30 +247,68 @@ def run_ours(args):
             torch.cuda.synchronize(device)
             return time_events(lambda i: g.replay(), 5, stream) / n_it
 
-    with torch.cuda.stream(stream):
-        for i in range(5):
-            embed(i); mlp(i)
-        torch.cuda.synchronize(device)
-    n_it = 64
-    t_embed = graph_time(embed, n_it)
-    t_mlp = graph_time(mlp, n_it)
     pk = peaks()
-    embed_bytes = ALG_BYTES_PER_SAMPLE * B + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4
-    stage = {
-        "embed_fwfm": dict(ms=t_embed, bound="hbm", achieved=embed_bytes / (t_embed * 1e-3) / 1e9, peak=pk["hbm"],
-                           unit="GB/s"),
-        "mlp": dict(ms=t_mlp, bound="tensor", achieved=MLP_FLOPS_PER_SAMPLE * B / (t_mlp * 1e-3) / 1e12,
-                    peak=pk["tf_burst"], unit="TFLOP/s"),
-    }
-    dom = "mlp" if t_mlp >= t_embed else "embed_fwfm"
+    n_it = 64
+    fused = bool(lib.dfw_fused_supported(plan.model_ref, prec)) and not os.environ.get("DFW_NO_FUSED")
+    step_bytes = ALG_BYTES_PER_SAMPLE * B + ALG_BYTES_PER_BATCH
+    if fused:
+        # one kernel per step: gather + FwFM (HBM/L2 side) and the MLP (tensor side) overlap inside it
+        t_f = graph_time(step, n_it)
+        stage = {
+            "fused_forward": dict(ms=t_f, bound="tensor", achieved=MLP_FLOPS_PER_SAMPLE * B / (t_f * 1e-3) / 1e12,
+                                  peak=pk["tf_burst"], unit="TFLOP/s"),
+            "fused_forward_hbm_view": dict(ms=t_f, bound="hbm", achieved=step_bytes / (t_f * 1e-3) / 1e9, peak=pk["hbm"],
+                                           unit="GB/s"),
+        }
+        dom = "fused_forward"
+    else:
+        FK = FIELD * K_EMB
+        ldE, ldEb = (FK + 3) // 4 * 4, (FK + 7) // 8 * 8
+        Bp = (B + 127) // 128 * 128
+        E = torch.zeros(Bp, ldE, device=device)
+        Eb = torch.zeros(Bp, ldEb, device=device, dtype=torch.bfloat16)
+        shallow = torch.zeros(Bp, device=device)
+        mws = torch.zeros(lib.dfw_mlp_workspace_bytes(plan.model_ref, B, prec) + 4096, dtype=torch.uint8, device=device)
+        bf = args.precision == "bf16"
+
+        def embed(i):
+            j = i % nb
+            rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B,
+                                    None if bf else E.data_ptr(), ldE, Eb.data_ptr() if bf else None, ldEb,
+                                    shallow.data_ptr(), None, sp)
+            if rc:
+                _lib.check(rc, "dfw_embed_fwfm")
+
+        mlp_fn = {"fp32": lib.dfw_mlp_fp32, "bf16x3": lib.dfw_mlp_fp32, "fp32_csr": lib.dfw_mlp_csr,
+                  "bf16": lib.dfw_mlp_bf16}[args.precision]
+
+        def mlp(i):
+            rc = mlp_fn(plan.model_ref, Eb.data_ptr() if bf else E.data_ptr(), ldEb if bf else ldE, B, shallow.data_ptr(),
+                        mws.data_ptr(), mws.numel(), logits[i % nb].data_ptr(), None, sp)
+            if rc:
+                _lib.check(rc, "dfw_mlp")
+
+        with torch.cuda.stream(stream):
+            for i in range(5):
+                embed(i); mlp(i)
+            torch.cuda.synchronize(device)
+        t_embed = graph_time(embed, n_it)
+        t_mlp = graph_time(mlp, n_it)
+        embed_bytes = ALG_BYTES_PER_SAMPLE * B + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4
+        stage = {
+            "embed_fwfm": dict(ms=t_embed, bound="hbm", achieved=embed_bytes / (t_embed * 1e-3) / 1e9, peak=pk["hbm"],
+                               unit="GB/s"),
+            "mlp": dict(ms=t_mlp, bound="tensor", achieved=MLP_FLOPS_PER_SAMPLE * B / (t_mlp * 1e-3) / 1e12,
+                        peak=pk["tf_burst"], unit="TFLOP/s"),
+        }
+        dom = "mlp" if t_mlp >= t_embed else "embed_fwfm"
     d = stage[dom]
     roofline = dict(kernel=dom, bound=d["bound"], achieved=round(d["achieved"], 3), peak=d["peak"], unit=d["unit"],
                     frac=round(d["achieved"] / d["peak"], 5), traffic=None, peak_source=pk["src"],
                     ms_per_launch=round(d["ms"], 5),
                     stages={k: dict(ms=round(v["ms"], 5), achieved=round(v["achieved"], 3), unit=v["unit"],
                                     frac=round(v["achieved"] / v["peak"], 5)) for k, v in stage.items()},
-                    whole_step_hbm_frac=round((ALG_BYTES_PER_SAMPLE * B + ALG_BYTES_PER_BATCH) / (ms_per_step * 1e-3)
-                                              / 1e9 / pk["hbm"], 5))
+                    whole_step_hbm_frac=round(step_bytes / (ms_per_step * 1e-3) / 1e9 / pk["hbm"], 5))
 
     # ---- e2e: host buffers through dfw_forward_host ------------------------------------------------------
     nh = 16
@@ -338,7 +352,9 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "fp32_csr": "f32", "bf16": "bf16 operands, f32 accumulate (shallow part f32)"}[args.precision],
+            "dtype": {"fp32": "f32", "fp32_csr": "f32", "bf16": "bf16 operands, f32 accumulate (shallow part f32)",
+                      "bf16x3": "f32 (MLP products as 3 split-bf16 tcgen05 MMAs with f32 accumulate, inside the fp32 "
+                                "parity bound 1e-5*max|logit|; gather/FwFM in f32)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "BASELINE config 2: DeepFwFM dense (fwfm+deep+fwlw), F=39 (13 numeric), K=10, MLP "
                                    "400x400x400, paper-Criteo cardinalities (1.33 M rows, 53 MB fp32), uniform indices",

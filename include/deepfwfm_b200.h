@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DFW_ABI_VERSION 2
+#define DFW_ABI_VERSION 3
 #define DFW_MAX_DEPTH 8
 #define DFW_MAX_FIELDS 64
 #define DFW_MAX_K 32
@@ -116,6 +116,9 @@ typedef struct dfw_model {
     const void* Wbf16_lo[DFW_MAX_DEPTH]; /* lo part bf16(W - hi) from dfw_pack_mlp_bf16_split (DFW_PREC_BF16X3), or NULL */
     dfw_csr csr[DFW_MAX_DEPTH];     /* dfw_csr_build image of W[l] (row_ptr NULL if absent)  */
     const void* shallow_image;      /* dfw_pack_shallow image (DEVICE), or NULL: dfw_forward then packs per call */
+    const float* field_cov_host;    /* HOST copy of field_cov.weight (F, F) taken when the plan was built, or NULL.  Derived
+                                       data like the shallow image: with it the fused kernel receives the symmetrised field
+                                       matrix as a kernel parameter (constant bank) instead of reading it from shared memory */
 } dfw_model;
 
 /* ---- library ---------------------------------------------------------------------------- */

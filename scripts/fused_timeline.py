@@ -17,7 +17,8 @@ plan = m._get_plan(); plan.ensure_image(m, prec)
 Xi, Xv = bench.make_batches(dev, synth.CRITEO_PAPER, B, 4, seed=0)
 out = torch.zeros(B, device=dev)
 nc = min((B + 31) // 32, 148)
-clk = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
+NCLK = 128
+clk = torch.zeros(148 * NCLK, dtype=torch.int64, device=dev)
 fn = lib.dfw_debug_set_fused_clock_buffer; fn.argtypes = [ctypes.c_void_p]; fn.restype = None
 st = torch.cuda.current_stream().cuda_stream
 def run(j=0):
@@ -27,7 +28,7 @@ def run(j=0):
 for j in range(3): run(j)
 torch.cuda.synchronize()
 fn(clk.data_ptr()); run(3); torch.cuda.synchronize(); fn(None)
-c = clk.cpu().numpy().reshape(148, 32)[:nc].astype(np.float64)
+c = clk.cpu().numpy().reshape(148, NCLK)[:nc].astype(np.float64)
 t0 = c[:, 0:1]          # MMA thread reaches the x_ready wait
 rel = c - t0
 names = {20: "gather done (E block)", 21: "X0 converted", 1: "x_ready seen by MMA", 22: "shallow done", 16: "tile done"}
@@ -39,3 +40,6 @@ order = [20, 21, 1, 8, 2, 9, 10, 3, 11, 12, 4, 13, 22, 16]
 print(f"B={B} {prec}: cycles relative to the MMA thread's start (median over {nc} CTAs / min / max)")
 for k in order:
     print(f"  {names[k]:24s} {np.median(rel[:, k]):9.0f} {rel[:, k].min():9.0f} {rel[:, k].max():9.0f}")
+
+print("gather group phases (median): start, image+idx regs, idx in smem, rows issued, E complete, interact start, phase D done")
+print("  " + " ".join(f"{np.median(rel[:, 96 + k]):9.0f}" for k in range(7)))

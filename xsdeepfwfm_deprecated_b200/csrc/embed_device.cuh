@@ -185,9 +185,18 @@ __device__ __forceinline__ void fixup_rows(const GatherCtx& g, bool any_qr) {
     }
 }
 
-// Phase-D ownership: thread `tid` of the group owns sample tid % S and, in round r, embedding column
-// tid / S + r * (nthreads / S).  R = number of rounds the group needs to cover K columns.
-template <int S> __device__ __forceinline__ int owner_col(int tid, int nthreads, int r) { return tid / S + r * (nthreads / S); }
+// Phase-D ownership: thread `tid` of the group owns one sample and, in round r, one embedding column.  A warp always
+// covers 16 samples x 2 adjacent columns: with the E pitch == 2 (mod 32) its column reads hit 32 distinct banks.
+//   S = 16: sample tid % 16, column tid / 16                       (+ r * nthreads / 16)
+//   S = 32: sample tid % 16 + 16 * (warp % 2), column (tid / 16) % 2 + 2 * (warp / 2)   (+ r * nthreads / 32)
+template <int S> __device__ __forceinline__ int owner_sample(int tid) {
+    if constexpr (S == 32) return (tid & 15) + (((tid >> 5) & 1) << 4);
+    else return tid % S;
+}
+template <int S> __device__ __forceinline__ int owner_col(int tid, int nthreads, int r) {
+    if constexpr (S == 32) return ((tid >> 4) & 1) + 2 * (tid >> 6) + r * (nthreads / S);
+    else return tid / S + r * (nthreads / S);
+}
 
 // ------------------------------------------------------------------------------------------ phases A + B
 // Fills sm.E (S x EP, rows >= nrows zeroed), sm.idx, sm.xv for samples [b0, b0 + nrows).  Returns through
@@ -294,7 +303,7 @@ __device__ __forceinline__ void embed_gather(const EmbedParams& p, const TileSme
     }
 
     // first-order table values of this thread's fields f = kk, kk+K, ...   (model/DeepFMs.py:300-309)
-    const int smp = tid % S;
+    const int smp = owner_sample<S>(tid);
     const bool live_sample = smp < nrows;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -335,9 +344,14 @@ __device__ __forceinline__ void embed_gather(const EmbedParams& p, const TileSme
 
 // ------------------------------------------------------------------------------------------ phases D + E
 // shallow_dst[s] = sum(first) + sum(second) + bias for s < nrows (any address space).
-template <int FT, int KT, int S, int R, int BAR>
+// cU != nullptr (dense unrolled path only): U is read from there with compile-time offsets -- the fused kernel passes its
+// __grid_constant__ parameter copy, so every U_ij becomes a constant-bank operand of its FFMA and phase D issues no
+// shared-memory loads for the field matrix (a broadcast LDS.128 still costs 4 register-write cycles per warp).
+// CONSTU (fused kernel): the dense path takes U only from cU; without it the kernel walks the pair list.
+template <int FT, int KT, int S, int R, int BAR, bool CONSTU = false>
 __device__ __forceinline__ void embed_interact(const EmbedParams& p, const TileSmem& sm, int tid, int nthreads, int nrows,
-                                                const float (&first_acc)[R], float* shallow_dst, long long* clk) {
+                                                const float (&first_acc)[R], float* shallow_dst, long long* clk,
+                                                const float* cU = nullptr) {
     const int F = FT > 0 ? FT : p.F;
     const int K = KT > 0 ? KT : p.K;
     const ImgLayout IL = img_layout(F, K);
@@ -350,8 +364,8 @@ __device__ __forceinline__ void embed_interact(const EmbedParams& p, const TileS
     const int EP = sm.EP;
     const bool fwlw = p.flags & DFW_USE_FWLW;
     const int P = F * (F - 1) / 2;
-    const bool use_list = (FT == 0) || (hdr->live * 6 < P);
-    const int smp = tid % S;
+    const bool use_list = (FT == 0) || (hdr->live * 6 < P) || (CONSTU && cU == nullptr);
+    const int smp = owner_sample<S>(tid);
     DFW_CLK(5);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -384,6 +398,28 @@ __device__ __forceinline__ void embed_interact(const EmbedParams& p, const TileS
             if (q < n) {
                 const PairEnt a = sPairs[q];
                 s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
+            }
+            second = s0 + s1;
+        } else if constexpr (FT > 0 && CONSTU) {
+            // second = sum_j e_j * (sum_{i<j} U_ij e_i): every U_ij is a constant-bank operand, 4 independent chains per j
+            constexpr int FTc = FT > 0 ? FT : 2, KTc = KT > 0 ? KT : 1;
+            float e[FTc];
+#pragma unroll
+            for (int f = 0; f < FTc; ++f) e[f] = myE[f * KTc];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 1; j < FTc; ++j) {
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < j; ++i) {
+                    const float u = cU[ucol_off(j) + i];
+                    if ((i & 3) == 0) d0 = fmaf(u, e[i], d0);
+                    else if ((i & 3) == 1) d1 = fmaf(u, e[i], d1);
+                    else if ((i & 3) == 2) d2 = fmaf(u, e[i], d2);
+                    else d3 = fmaf(u, e[i], d3);
+                }
+                const float dot = (d0 + d1) + (d2 + d3);
+                if (j & 1) s0 = fmaf(e[j], dot, s0); else s1 = fmaf(e[j], dot, s1);
             }
             second = s0 + s1;
         } else if constexpr (FT > 0) {

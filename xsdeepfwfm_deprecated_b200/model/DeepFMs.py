@@ -152,6 +152,9 @@ class _Plan:
             _lib.check(lib.dfw_pack_shallow(self.model_ref, self.shallow_image.data_ptr(), _stream_ptr(dev)),
                        "dfw_pack_shallow")
         m.shallow_image = self.shallow_image.data_ptr()
+        if owner.use_fwfm:      # host snapshot of field_cov: the fused kernel takes the field matrix as a kernel parameter
+            self.field_cov_host = owner.field_cov.weight.detach().to("cpu", torch.float32).contiguous()
+            m.field_cov_host = self.field_cov_host.data_ptr()
         self.images = set()     # which derived images exist: "bf16", "csr"
         self.workspace = None
         self.host_ws = None
