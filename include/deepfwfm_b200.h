@@ -214,6 +214,15 @@ int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, const float* xv
                      int precision, void* workspace, size_t workspace_bytes, float* logits_host,
                      float* prob_host, void* stream);
 
+/* N samples in (pinned) host memory as batches of `batch` samples, round-robin over internal streams so that the H2D copy of
+ * batch i+1 overlaps the kernels of batch i and the D2H of batch i-1; ONE host synchronisation at the end.  The streamed
+ * form of eval_by_batch / predict_proba (model/DeepFMs.py:750-784, 864-873).  Results are identical to N/batch calls of
+ * dfw_forward_host.  workspace: dfw_forward_host_stream_workspace_bytes(m, batch, precision). */
+size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, int64_t batch, int precision);
+int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t N, int64_t batch,
+                            int precision, void* workspace, size_t workspace_bytes, float* logits_host, float* prob_host,
+                            void* stream);
+
 /* ---- multi-GPU: row-sharded tables ------------------------------------------- */
 /* cudaMalloc'ed shard storage that can be exported to peers of the same node. */
 int dfw_shard_alloc(size_t bytes, void** dev_ptr);

@@ -368,3 +368,19 @@ def test_config3_pruned_and_config5_twitter_bf16x3():
     ref = closed_form.forward(c["cfg"], c["weights"], Xi, Xv)["logit"]
     got = run(to_cuda(c["cfg"], c["weights"], precision="bf16x3"), Xi, Xv)
     assert np.abs(got - ref).max() <= logit_tol(ref, FP32_REL)
+
+
+def test_streamed_host_inference_matches_forward():
+    """dfw_forward_host_stream (3 rotating streams, ragged last batch) == forward + sigmoid, for every precision."""
+    c = load_case("deepfwfm_fwlw")
+    cfg = c["cfg"]
+    Xi, Xv = synth.make_inputs(cfg, 5000, seed=21)
+    for precision in ("fp32", "bf16x3", "bf16"):
+        m = to_cuda(cfg, c["weights"], precision=precision)
+        with torch.no_grad():
+            logits, prob = m(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda(), return_prob=True)
+        got_p, got_l = m.predict_proba_host(Xi, Xv, batch_size=512, want_logits=True, batches_in_flight=4)
+        assert np.array_equal(got_l, logits.cpu().numpy()), precision
+        assert np.array_equal(got_p, prob.cpu().numpy()), precision
+        got_p2 = m.predict_proba_host(Xi, Xv, batch_size=8192)
+        assert np.array_equal(got_p2, got_p), precision

@@ -190,6 +190,89 @@ extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, cons
     return 0;
 }
 
+// ---- streamed host-buffer inference --------------------------------------------------------------
+// N samples in pinned host memory, processed as batches of `batch` round-robin over kSlots internal streams: batch i+1's
+// H2D copy overlaps batch i's kernels and batch i-1's D2H, one host synchronisation at the end.  This is what
+// eval_by_batch / predict_proba do around forward (model/DeepFMs.py:750-784, 864-873) without their per-batch
+// .cuda() / .cpu() round trips.
+namespace {
+constexpr int kSlots = 3;
+struct HostPipe {
+    cudaStream_t streams[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
+    cudaEvent_t start = nullptr;
+    int device = -1;
+};
+thread_local HostPipe g_pipe[8];
+
+int get_pipe(HostPipe** out) {
+    int dev = 0;
+    DFW_CUDA_OK(cudaGetDevice(&dev));
+    DFW_REQUIRE(dev >= 0 && dev < 8, DFW_E_UNSUPPORTED, "device ordinal %d >= 8", dev);
+    HostPipe& hp = g_pipe[dev];
+    if (hp.device != dev) {
+        for (int i = 0; i < kSlots; ++i) {
+            DFW_CUDA_OK(cudaStreamCreateWithFlags(&hp.streams[i], cudaStreamNonBlocking));
+            DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+        }
+        DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.start, cudaEventDisableTiming));
+        hp.device = dev;
+    }
+    *out = &hp;
+    return 0;
+}
+}  // namespace
+
+extern "C" size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, int64_t batch, int precision) {
+    if (!m || batch <= 0) return 256;
+    return kSlots * align_up(host_layout(m, batch, precision).total, 256);
+}
+
+extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t N,
+                                       int64_t batch, int precision, void* workspace, size_t workspace_bytes,
+                                       float* logits_host, float* prob_host, void* stream) {
+    if (int rc = check_model(m)) return rc;
+    if (N <= 0) return 0;
+    DFW_REQUIRE(batch > 0, DFW_E_ARG, "batch must be positive");
+    DFW_REQUIRE(logits_host || prob_host, DFW_E_ARG, "no output requested");
+    const HostLayout H = host_layout(m, batch, precision);
+    const size_t slot_bytes = align_up(H.total, 256);
+    DFW_REQUIRE(workspace && workspace_bytes >= kSlots * slot_bytes, DFW_E_WORKSPACE,
+                "streamed host-forward workspace too small: %zu < %zu", workspace_bytes, kSlots * slot_bytes);
+    DFW_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, DFW_E_ARG, "workspace must be 256-byte aligned");
+    HostPipe* hp = nullptr;
+    if (int rc = get_pipe(&hp)) return rc;
+    cudaStream_t main_st = reinterpret_cast<cudaStream_t>(stream);
+    const int C = m->field_size - m->numerical, num = m->numerical;
+    // the internal streams start after everything already queued on the caller's stream (weights, images)
+    DFW_CUDA_OK(cudaEventRecord(hp->start, main_st));
+    for (int i = 0; i < kSlots; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
+    int64_t done = 0;
+    for (int64_t i = 0; done < N; ++i, done += batch) {
+        const int64_t b = N - done < batch ? N - done : batch;
+        const int slot = (int)(i % kSlots);
+        cudaStream_t st = hp->streams[slot];
+        char* ws = static_cast<char*>(workspace) + (size_t)slot * slot_bytes;
+        int64_t* xi = reinterpret_cast<int64_t*>(ws + H.oXi);
+        float* xv = reinterpret_cast<float*>(ws + H.oXv);
+        float* logit = reinterpret_cast<float*>(ws + H.oLogit);
+        float* prob = reinterpret_cast<float*>(ws + H.oProb);
+        if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host + done * C, (size_t)b * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, b, precision, ws + H.oFwd, slot_bytes - H.oFwd,
+                                 logits_host ? logit : nullptr, prob_host ? prob : nullptr, nullptr, st))
+            return rc;
+        if (logits_host) DFW_CUDA_OK(cudaMemcpyAsync(logits_host + done, logit, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (prob_host) DFW_CUDA_OK(cudaMemcpyAsync(prob_host + done, prob, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));
+        DFW_CUDA_OK(cudaStreamWaitEvent(main_st, hp->done[i], 0));
+    }
+    DFW_CUDA_OK(cudaStreamSynchronize(main_st));
+    return 0;
+}
+
 // ---- multi-GPU helpers -------------------------------------------------------------------------
 extern "C" int dfw_shard_alloc(size_t bytes, void** dev_ptr) {
     DFW_REQUIRE(dev_ptr, DFW_E_ARG, "dev_ptr is NULL");

@@ -510,9 +510,10 @@ class DeepFMs(nn.Module):
 
     # ------------------------------------------------------------------ host-buffer inference (e2e path)
     def predict_proba_host(self, Xi_np: np.ndarray, Xv_np: np.ndarray, batch_size: int = 8192,
-                           want_logits: bool = False):
-        """numpy in, numpy out through ``dfw_forward_host``: pinned staging, H2D, fused forward +
-        sigmoid, D2H -- what eval_by_batch / predict_proba do around forward (model/DeepFMs.py:771-777)."""
+                           want_logits: bool = False, batches_in_flight: int = 16):
+        """numpy in, numpy out through ``dfw_forward_host_stream``: pinned staging, then per batch H2D, fused forward +
+        sigmoid, D2H on rotating streams (copies overlap kernels), one synchronisation per ``batches_in_flight``
+        batches -- what eval_by_batch / predict_proba do around forward (model/DeepFMs.py:771-777)."""
         plan = self._get_plan()
         dev = plan.device
         lib = _lib.load()
@@ -523,28 +524,29 @@ class DeepFMs(nn.Module):
         Xi_np = np.ascontiguousarray(np.asarray(Xi_np, dtype=np.int64).reshape(n, C_))
         Xv_np = np.ascontiguousarray(np.asarray(Xv_np, dtype=np.float32).reshape(n, -1)[:, :self.num])
         bs = min(batch_size, max(n, 1))
-        if plan.host_ws is None or plan.host_ws[0] < bs or plan.host_ws[1] != prec:
-            nbytes = lib.dfw_forward_host_workspace_bytes(plan.model_ref, bs, prec)
-            plan.host_ws = (bs, prec, torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev),
-                            torch.empty(bs * C_, dtype=torch.int64).pin_memory(),
-                            torch.empty(bs * max(self.num, 1), dtype=torch.float32).pin_memory(),
-                            torch.empty(bs, dtype=torch.float32).pin_memory(),
-                            torch.empty(bs, dtype=torch.float32).pin_memory())
-        _, _, ws, pxi, pxv, pprob, plogit = plan.host_ws
+        chunk = bs * max(1, min(batches_in_flight, -(-max(n, 1) // bs)))
+        if plan.host_ws is None or plan.host_ws[0] != bs or plan.host_ws[1] != prec or plan.host_ws[2] < chunk:
+            nbytes = lib.dfw_forward_host_stream_workspace_bytes(plan.model_ref, bs, prec)
+            plan.host_ws = (bs, prec, chunk, torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev),
+                            torch.empty(chunk * C_, dtype=torch.int64).pin_memory(),
+                            torch.empty(chunk * max(self.num, 1), dtype=torch.float32).pin_memory(),
+                            torch.empty(chunk, dtype=torch.float32).pin_memory(),
+                            torch.empty(chunk, dtype=torch.float32).pin_memory())
+        _, _, chunk, ws, pxi, pxv, pprob, plogit = plan.host_ws
         out = np.empty(n, dtype=np.float32)
         out_logit = np.empty(n, dtype=np.float32) if want_logits else None
         st = _stream_ptr(dev)
         with torch.cuda.device(dev):
-            for o in range(0, n, bs):
-                e = min(n, o + bs)
+            for o in range(0, n, chunk):
+                e = min(n, o + chunk)
                 b = e - o
                 pxi.numpy()[:b * C_] = Xi_np[o:e].ravel()
                 if self.num:
                     pxv.numpy()[:b * self.num] = Xv_np[o:e].ravel()
-                rc = lib.dfw_forward_host(plan.model_ref, pxi.data_ptr(), pxv.data_ptr(), b, prec, ws.data_ptr(),
-                                          ws.numel(), plogit.data_ptr() if want_logits else None,
-                                          pprob.data_ptr(), st)
-                _lib.check(rc, "dfw_forward_host")
+                rc = lib.dfw_forward_host_stream(plan.model_ref, pxi.data_ptr(), pxv.data_ptr(), b, bs, prec,
+                                                 ws.data_ptr(), ws.numel(), plogit.data_ptr() if want_logits else None,
+                                                 pprob.data_ptr(), st)
+                _lib.check(rc, "dfw_forward_host_stream")
                 out[o:e] = pprob.numpy()[:b]
                 if want_logits:
                     out_logit[o:e] = plogit.numpy()[:b]
