@@ -27,7 +27,10 @@ def run(j=0):
     _lib.check(rc, "dfw_forward_fused")
 for j in range(3): run(j)
 torch.cuda.synchronize()
-fn(clk.data_ptr()); run(3); torch.cuda.synchronize(); fn(None)
+fn(clk.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(3); run(0); run(1); run(2); e1.record(); torch.cuda.synchronize(); fn(None)
+print(f"4 back-to-back launches: {e0.elapsed_time(e1) * 250:.1f} us per launch (CUDA events)")
 c = clk.cpu().numpy().reshape(148, NCLK)[:nc].astype(np.float64)
 t0 = c[:, 0:1]          # MMA thread reaches the x_ready wait
 rel = c - t0
@@ -43,3 +46,7 @@ for k in order:
 
 print("gather group phases (median): start, image+idx regs, idx in smem, rows issued, E complete, interact start, phase D done")
 print("  " + " ".join(f"{np.median(rel[:, 96 + k]):9.0f}" for k in range(7)))
+
+print(f"kernel entry -> MMA thread start: median {np.median(-rel[:, 28]):.0f} cycles; MMA start -> exit: {np.median(rel[:, 30]):.0f} cycles")
+g0, g1 = c[:, 29], c[:, 31]
+print(f"globaltimer: first CTA entry -> last CTA exit {g1.max() - g0.min():.0f} ns; CTA entry spread {g0.max() - g0.min():.0f} ns; per-CTA lifetime median {np.median(g1 - g0):.0f} ns")

@@ -8,7 +8,7 @@
 namespace dfw { void set_error(const char* f, ...) { printf("error: %s\n", f); } std::atomic<long long> g_launches{0}; }
 using namespace dfw::tc;
 
-__global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap map, int boxes, int nstage, int cl, int rows_total, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap map, int boxes, int nstage, int cl, int box_rows, long long* out) {
     extern __shared__ unsigned char raw[];
     unsigned char* base = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full[12], empty[12];
@@ -21,18 +21,20 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap 
     if (cl > 1) cluster_sync_all();
     const uint32_t crank = cl > 1 ? cluster_ctarank() : 0;
     const uint16_t mask = (uint16_t)((1u << cl) - 1);
-    const int per = 128 / cl;
+    const int per = box_rows / cl;
+    const uint32_t box_bytes = (uint32_t)box_rows * 128u;
     long long t0 = clock64();
     if (warp == 0) {
         uint32_t st = 0, ph = 0;
+        int mt = 0, c = 0;                                             // 3 neuron tiles x 7 K chunks of one 400 x 448 layer image
         for (int b = 0; b < boxes; ++b) {
-            const int tile = b % 21, mt = tile / 7, c = tile % 7;      // 3 neuron tiles x 7 K chunks of one 400 x 448 layer image
+            if (++c == 7) { c = 0; if (++mt == 3) mt = 0; }
             mbar_wait(&empty[st], ph ^ 1, nullptr, 0);
             if (elect_one()) {
-                mbar_expect_tx(&full[st], 16384);
-                unsigned char* dst = base + st * 16384 + crank * per * 128;
-                if (cl > 1) tma_load_2d_mc(dst, &map, &full[st], c * 64, mt * 128 + (int)crank * per, mask);
-                else tma_load_2d(dst, &map, &full[st], c * 64, mt * 128);
+                mbar_expect_tx(&full[st], box_bytes);
+                unsigned char* dst = base + st * box_bytes + crank * per * 128;
+                if (cl > 1) tma_load_2d_mc(dst, &map, &full[st], c * 64, mt * box_rows + (int)crank * per, mask);
+                else tma_load_2d(dst, &map, &full[st], c * 64, mt * box_rows);
             }
             __syncwarp();
             if (++st == (uint32_t)nstage) { st = 0; ph ^= 1; }
@@ -41,15 +43,13 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap 
         uint32_t st = 0, ph = 0;
         for (int b = 0; b < boxes; ++b) {
             mbar_wait(&full[st], ph, nullptr, 0);
-            if (lane == 0) {
-                if (cl > 1) {
-                    for (int r = 0; r < cl; ++r) {       // release the stage in every CTA of the cluster
-                        uint32_t remote;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&empty[st])), "r"(r));
-                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-                    }
-                } else mbar_arrive(&empty[st]);
-            }
+            if (cl > 1) {
+                if (lane < cl) {                     // release the stage in every CTA of the cluster
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&empty[st])), "r"(lane));
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+                }
+            } else if (lane == 0) mbar_arrive(&empty[st]);
             __syncwarp();
             if (++st == (uint32_t)nstage) { st = 0; ph ^= 1; }
         }
@@ -61,26 +61,26 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap 
 }
 
 int main() {
-    const int rows = 400, cols = 448;
+    const int rows = 768, cols = 448;
     void* W; cudaMalloc(&W, rows * cols * 2); cudaMemset(W, 0, rows * cols * 2);
     long long* d; cudaMalloc(&d, 148 * 8);
     const int SM = 12 * 16384 + 2048;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
     const int boxes = 21 * 20;
-    for (int cl : {1, 2, 4}) for (int nstage : {4, 7, 12}) for (int grid : {4, 128}) {
+    for (int cl : {1, 4}) for (int box_rows : {64, 128, 256}) for (int nstage : {6}) for (int grid : {128}) {
         CUtensorMap map;
-        if (make_map(&map, W, rows, cols, cols, 128 / cl)) return 1;
+        if (make_map(&map, W, rows, cols, cols, box_rows / cl)) return 1;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = SM;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, k, map, boxes, nstage, cl, rows, d);
+        for (int rep = 0; rep < 2; ++rep) cudaLaunchKernelEx(&cfg, k, map, boxes, nstage, cl, box_rows, d);
         std::vector<long long> h(grid);
         cudaError_t e = cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
-        printf("cluster %d  stages %2d  grid %3d : %8lld cycles for %d KB per SM -> %6.1f B/clk/SM\n", cl, nstage, grid, mx, boxes * 16, boxes * 16384.0 / mx);
+        printf("cluster %d  box %3d rows  stages %2d  grid %3d : %8lld cycles (%5.0f per box) -> %6.1f B/clk/SM\n", cl, box_rows, nstage, grid, mx, (double)mx / boxes, boxes * box_rows * 128.0 / mx);
     }
     return 0;
 }

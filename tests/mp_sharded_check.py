@@ -26,12 +26,14 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for tag, kw in (("plain", {}), ("qr", dict(qr_flag=1, qr_collisions=4, qr_threshold=200))):
+    for tag, kw, precision in (("plain", {}, "fp32"), ("qr", dict(qr_flag=1, qr_collisions=4, qr_threshold=200), "fp32"),
+                               ("plain", {}, "bf16x3"), ("qr", dict(qr_flag=1, qr_collisions=4, qr_threshold=200), "bf16x3")):
         cfg = PathConfig(39, SIZES, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, deep_nodes=64, **kw)
         w = synth.make_weights(cfg, seed=5)
         Xi, Xv = synth.make_inputs(cfg, 777 + 13 * rank, seed=50 + rank)          # ragged, different per rank
         tXi, tXv = torch.from_numpy(Xi).to(dev), torch.from_numpy(Xv).to(dev)
-        common = dict(use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, deep_nodes=64, use_cuda=True, **kw)
+        common = dict(use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, deep_nodes=64, use_cuda=True,
+                      precision=precision, **kw)
         base = DeepFMs(39, SIZES, **common)
         base.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
         base = base.to(dev).eval()
@@ -48,7 +50,7 @@ def main():
             with torch.no_grad():
                 got = m(tXi, tXv)
             same = bool(torch.equal(got, want))
-            print(f"[rank {rank}/{world}] {tag:5s} {exchange:4s} sharded_tables={nsh} bit_identical={same}", flush=True)
+            print(f"[rank {rank}/{world}] {tag:5s} {precision:6s} {exchange:4s} sharded_tables={nsh} bit_identical={same}", flush=True)
             ok &= same and nsh >= 4
             m.release()
     t = torch.tensor([1 if ok else 0], device=dev)

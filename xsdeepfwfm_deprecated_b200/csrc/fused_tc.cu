@@ -131,6 +131,10 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = p.depth, NSTAGE = p.nstage, CL = p.cluster;
+    if (p.clk && threadIdx.x == 0) {           // debug timeline: kernel entry in SM clocks and in the global ns timer
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.clk[blockIdx.x * FZ_NCLK + 28] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 29] = (long long)t;
+    }
     const uint16_t cmask = (uint16_t)((1u << CL) - 1);
 
     if (threadIdx.x == 0) {
@@ -173,22 +177,38 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                     const int row0 = mt * 128 + (int)crank * per;
                     const uint32_t bytes = (uint32_t)(rows * 128);
                     const int which = rows == 64 ? 1 : 0;
-                    for (int c = 0; c < kch; ++c) {
-#pragma unroll
-                        for (int h = 0; h < (SPLIT ? 2 : 1); ++h) {
-                            FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | h | (1 << 24));
-                            mbar_wait(&bars->empty[stage], sphase ^ 1, p.err, 12);
-                            FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | h | (2 << 24));
-                            unsigned char* dst = sW + (size_t)stage * STAGE_BYTES + dst_off;
-                            const CUtensorMap* map = &maps.w[l][h][which];
-                            if (elect_one()) {
-                                mbar_expect_tx(&bars->full[stage], bytes);
-                                if (CL > 1) tma_load_2d_mc(dst, map, &bars->full[stage], c * KCH, row0, cmask);
-                                else tma_load_2d(dst, map, &bars->full[stage], c * KCH, row0);
+                    // two boxes per iteration (hi + lo of one chunk, or two chunks): both empty-barrier probes are issued
+                    // before either is resolved, so the ~100-cycle probe latency is paid once per 32 KB, not per 16 KB
+                    constexpr int CPG = SPLIT ? 1 : 2;              // K chunks per iteration
+                    for (int c = 0; c < kch; c += CPG) {
+                        const bool two = SPLIT || (c + 1 < kch);
+                        const uint32_t s0 = stage, ph0 = sphase;
+                        uint32_t s1 = s0 + 1, ph1 = ph0;
+                        if (s1 == (uint32_t)NSTAGE) { s1 = 0; ph1 ^= 1; }
+                        const bool r0 = mbar_try(&bars->empty[s0], ph0 ^ 1);
+                        const bool r1 = two ? mbar_try(&bars->empty[s1], ph1 ^ 1) : true;
+                        FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | (1 << 24));
+                        if (!r0) mbar_wait(&bars->empty[s0], ph0 ^ 1, p.err, 12);
+                        if (!r1) mbar_wait(&bars->empty[s1], ph1 ^ 1, p.err, 13);
+                        FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | (2 << 24));
+                        unsigned char* dst0 = sW + (size_t)s0 * STAGE_BYTES + dst_off;
+                        unsigned char* dst1 = sW + (size_t)s1 * STAGE_BYTES + dst_off;
+                        const CUtensorMap* map0 = &maps.w[l][0][which];
+                        const CUtensorMap* map1 = &maps.w[l][SPLIT ? 1 : 0][which];
+                        const int c1 = SPLIT ? c : c + 1;
+                        if (elect_one()) {
+                            mbar_expect_tx(&bars->full[s0], bytes);
+                            if (CL > 1) tma_load_2d_mc(dst0, map0, &bars->full[s0], c * KCH, row0, cmask);
+                            else tma_load_2d(dst0, map0, &bars->full[s0], c * KCH, row0);
+                            if (two) {
+                                mbar_expect_tx(&bars->full[s1], bytes);
+                                if (CL > 1) tma_load_2d_mc(dst1, map1, &bars->full[s1], c1 * KCH, row0, cmask);
+                                else tma_load_2d(dst1, map1, &bars->full[s1], c1 * KCH, row0);
                             }
-                            __syncwarp();
-                            if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; }
                         }
+                        __syncwarp();
+                        stage = s1; sphase = ph1;
+                        if (two) { if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; } }
                     }
                 }
             }
@@ -211,41 +231,60 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                     const int rows = mtile_rows(npad, mt);
                     const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + mt * NB);
                     const uint32_t idesc = make_idesc(rows, NB), idesc_lo = make_idesc(rows, 32);
-                    for (int c = 0; c < kch; ++c) {
+                    constexpr int CPG = SPLIT ? 1 : 2;              // K chunks per iteration (two ring stages either way)
+                    for (int c = 0; c < kch; c += CPG) {
                         if (mt == 0) {
                             if (l == 0) {
                                 if (c == 0) { if (it == 0 && lane == 0) FZ_CLK(0); mbar_wait(&bars->x_ready, (uint32_t)(it & 1), p.err, 21); if (it == 0 && lane == 0) FZ_CLK(1); }
                             } else if ((c & 1) == 0) {
-                                // chunk c holds neurons [64c, 64c+64) of the previous layer = its neuron tile c/2
+                                // chunks c, c+1 hold neurons [64c, 64c+128) of the previous layer = its neuron tile c/2
                                 const int g = c >> 1, bit = buf * MAX_MT + g;
                                 FZ_PROG(1, (l << 16) | (c << 8) | (5 << 24));
                                 mbar_wait(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
                                 act_bits ^= 1u << bit;
                             }
                         }
-                        const int ksteps = min(4, (K - c * KCH) / 16);
+                        const bool two = SPLIT || (c + 1 < kch);
+                        const int c1 = SPLIT ? c : c + 1;
+                        const int ks0 = min(4, (K - c * KCH) / 16), ks1 = two ? min(4, (K - c1 * KCH) / 16) : 0;
                         const uint64_t bdesc0 = make_desc_sw128(sXb + (uint32_t)(c * CH));
-#pragma unroll
-                        for (int h = 0; h < (SPLIT ? 2 : 1); ++h) {
-                            FZ_PROG(1, (l << 16) | (c << 8) | (mt << 4) | h | (3 << 24));
-                            mbar_wait(&bars->full[stage], sphase, p.err, 24);
-                            tc_fence_after();
-                            const uint64_t adesc0 = make_desc_sw128(sW_u32 + stage * (uint32_t)STAGE_BYTES);
-                            const uint32_t id = h ? idesc_lo : idesc;
-                            const uint32_t acc0 = (h | c) ? 1u : 0u;
-                            if (elect_one()) {
-                                umma_bf16(dcol, adesc0, bdesc0, id, acc0);               // +32 bytes (16 bf16) along K per step
-                                if (ksteps > 1) umma_bf16(dcol, adesc0 + 2, bdesc0 + 2, id, 1u);
-                                if (ksteps > 2) umma_bf16(dcol, adesc0 + 4, bdesc0 + 4, id, 1u);
-                                if (ksteps > 3) umma_bf16(dcol, adesc0 + 6, bdesc0 + 6, id, 1u);
-                                if (CL > 1) umma_commit_mc(&bars->empty[stage], cmask);   // this CTA is done with the stage (all CTAs are told)
-                                else umma_commit(&bars->empty[stage]);
-                                // accumulators of (layer l, neuron tile mt) complete after the last chunk
-                                if (c == kch - 1 && h == (SPLIT ? 1 : 0)) umma_commit(&bars->acc_full[buf][mt]);
+                        const uint64_t bdesc1 = make_desc_sw128(sXb + (uint32_t)(c1 * CH));
+                        const uint32_t s0 = stage, ph0 = sphase;
+                        uint32_t s1 = s0 + 1, ph1 = ph0;
+                        if (s1 == (uint32_t)NSTAGE) { s1 = 0; ph1 ^= 1; }
+                        // both probes in flight together; the blocking waits only run when the weights have not landed yet
+                        const bool r0 = mbar_try(&bars->full[s0], ph0);
+                        const bool r1 = two ? mbar_try(&bars->full[s1], ph1) : true;
+                        FZ_PROG(1, (l << 16) | (c << 8) | (mt << 4) | (3 << 24));
+                        if (!r0) mbar_wait(&bars->full[s0], ph0, p.err, 24);
+                        if (!r1) mbar_wait(&bars->full[s1], ph1, p.err, 25);
+                        tc_fence_after();
+                        const uint64_t adesc0 = make_desc_sw128(sW_u32 + s0 * (uint32_t)STAGE_BYTES);
+                        const uint64_t adesc1 = make_desc_sw128(sW_u32 + s1 * (uint32_t)STAGE_BYTES);
+                        const uint32_t id1 = SPLIT ? idesc_lo : idesc;
+                        const uint32_t acc0 = c ? 1u : 0u;
+                        const bool last_c = c1 == kch - 1 || c == kch - 1;
+                        if (elect_one()) {
+                            umma_bf16(dcol, adesc0, bdesc0, idesc, acc0);                  // +32 bytes (16 bf16) along K per step
+                            if (ks0 > 1) umma_bf16(dcol, adesc0 + 2, bdesc0 + 2, idesc, 1u);
+                            if (ks0 > 2) umma_bf16(dcol, adesc0 + 4, bdesc0 + 4, idesc, 1u);
+                            if (ks0 > 3) umma_bf16(dcol, adesc0 + 6, bdesc0 + 6, idesc, 1u);
+                            if (CL > 1) umma_commit_mc(&bars->empty[s0], cmask);           // this CTA is done with the stage (all CTAs are told)
+                            else umma_commit(&bars->empty[s0]);
+                            if (two) {
+                                umma_bf16(dcol, adesc1, bdesc1, id1, 1u);
+                                if (ks1 > 1) umma_bf16(dcol, adesc1 + 2, bdesc1 + 2, id1, 1u);
+                                if (ks1 > 2) umma_bf16(dcol, adesc1 + 4, bdesc1 + 4, id1, 1u);
+                                if (ks1 > 3) umma_bf16(dcol, adesc1 + 6, bdesc1 + 6, id1, 1u);
+                                if (CL > 1) umma_commit_mc(&bars->empty[s1], cmask);
+                                else umma_commit(&bars->empty[s1]);
                             }
-                            __syncwarp();
-                            if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; }
+                            // accumulators of (layer l, neuron tile mt) complete after the last chunk
+                            if (last_c) umma_commit(&bars->acc_full[buf][mt]);
                         }
+                        __syncwarp();
+                        stage = s1; sphase = ph1;
+                        if (two) { if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; } }
                     }
                     if (it == 0 && l < 4 && mt == MT - 1 && lane == 0) FZ_CLK(2 + l);
                 }
@@ -421,6 +460,10 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     __syncthreads();
     if (CL > 1) cluster_sync_all();    // no CTA exits while a peer may still multicast into it
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (p.clk && threadIdx.x == 32) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.clk[blockIdx.x * FZ_NCLK + 30] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 31] = (long long)t;
+    }
 }
 
 // fp32 (out, in) row-major -> bf16 hi (and lo = bf16(w - hi)) images (pad16(out), pad64(in)), zero padded

@@ -41,6 +41,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         }
     }
 }
+// one non-blocking probe: true if the phase with this parity has completed.  Two probes issued back to back overlap their
+// latency (~100 cycles each even when the barrier is long complete), which a chain of blocking waits cannot.
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
