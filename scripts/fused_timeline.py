@@ -34,7 +34,7 @@ print(f"4 back-to-back launches: {e0.elapsed_time(e1) * 250:.1f} us per launch (
 c = clk.cpu().numpy().reshape(148, NCLK)[:nc].astype(np.float64)
 t0 = c[:, 0:1]          # MMA thread reaches the x_ready wait
 rel = c - t0
-names = {20: "gather done (E block)", 21: "X0 converted", 1: "x_ready seen by MMA", 22: "shallow done", 16: "tile done"}
+names = {20: "gather done (E block)", 21: "X written (bf16)", 1: "x_ready seen by MMA", 22: "shallow done", 16: "tile done"}
 for l in range(3):
     names[2 + l] = f"L{l+1} all MMAs issued"
     names[8 + 2 * l] = f"L{l+1} first acc ready"

@@ -8,16 +8,22 @@
 // nn.Linear's (out, in) layout, K-major as stored) and the SAMPLES are N = 32, so a CTA owns 32 samples, B = 4096 is
 // 128 CTAs, and activations never leave the SM:  D_l^T (neurons x samples, TMEM) = W_l (smem, streamed) x X_l^T (smem).
 //
-//   CTA = 512 threads, one per SM, cluster of `cluster` CTAs sharing every weight box by TMA multicast:
-//     warp 0      TMA producer: streams (layer, 128-neuron tile, 64-wide K chunk) weight boxes through an mbarrier ring;
-//                 each CTA of the cluster fetches 1/cluster of the box's rows and multicasts it to all
-//     warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128 (64 for a short last tile), N = 32 / 64, K = 16;
-//                 the whole warp walks the loop and one elected lane issues (descriptors stay in uniform registers)
-//     warps 2-5   epilogue: thread = one neuron (TMEM lane); tcgen05.ld its 32 samples, + bias, ReLU, -> bf16 into the
-//                 next layer's operand buffer (K-major, 128B swizzle); last layer: dot with net_1_fc in registers,
-//                 warp-transpose reduction, + shallow, optional sigmoid -> global
-//     warps 6-15  gather group (embed_device.cuh): indices -> rows (cp.async) -> fix-ups -> bf16 operand of layer 1,
-//                 then first order + FwFM second order in fp32 while the tensor cores already run layer 1
+//   CTA = 576 threads, one per SM, cluster of `cluster` CTAs sharing every weight box by TMA multicast:
+//     warps 0-1   TMA producers, one per ring: stream (layer, 64-wide K chunk, 128-neuron tile[, hi/lo]) 16 KB weight boxes
+//                 into TWO mbarrier rings -- even neuron tiles into ring 0, odd tiles into ring 1; each CTA of the cluster
+//                 fetches 1/cluster of a box's rows and multicasts it to all
+//     warps 2-3   MMA issuers, one per ring: tcgen05.mma.cta_group::1.kind::f16, M = 128 (64 for a short last tile),
+//                 N = 32 / 64, K = 16.  The whole warp walks the loop and one elected lane issues (descriptors stay in
+//                 uniform registers).  K-outer order: chunk c of every tile, then chunk c+1, so the two warps' barrier
+//                 probes / commits (a few hundred cycles per stage) hide behind each other's MMAs.  One ring per warp keeps
+//                 every barrier's phases observed in order (1-bit parity waits are only safe that way).
+//     warps 4-7   epilogue: thread = one neuron (TMEM lane); tcgen05.ld its 32 samples, + bias, ReLU, -> bf16 (hi | lo) into
+//                 the activation buffer (K-major, 128B swizzle) for the next layer; last layer: x net_1_fc, warp
+//                 transpose-reduction, + shallow, optional sigmoid -> global
+//     warps 8-17  gather group (embed_device.cuh): indices -> rows (cp.async) -> fix-ups (fp32 block in shared memory);
+//                 each thread then takes its (sample, column) values into registers, the block is overwritten IN PLACE by
+//                 the bf16 operand of layer 1, and first order + FwFM second order run from the registers while the tensor
+//                 cores already work on layer 1
 //
 //   SPLIT = false ("bf16"):   operands rounded to bf16, fp32 accumulate -- the looser-bound path (5e-4 * max|logit|)
 //   SPLIT = true  ("bf16x3"): every fp32 operand is split x = hi + lo (two bf16), and the product is
@@ -26,7 +32,8 @@
 //                 golden cases).  X_hi and X_lo are stacked along N (one N = 64 MMA against W_hi), W_lo X_hi is a second
 //                 N = 32 MMA into the same accumulator columns: 2x the tensor time of bf16, not 3x.
 //
-//   Shared memory: X0 | X1 (activation ping-pong; the fp32 gather block aliases X1) | weight ring | shallow image | misc
+//   Shared memory: X (ONE activation buffer; K-outer order makes chunk c dead once every tile has consumed it, so layer l+1's
+//   input overwrites layer l's; the fp32 gather block aliases it) | ring 0 | ring 1 | shallow image | misc
 //   TMEM: 2 x 256 columns (layer parity) x (<= 4 neuron tiles x 32|64 sample columns)
 //   Limits of the fused form: depth <= 4, widths <= 512, F*K <= 512, K <= 20.  Other shapes take the staged path.
 #include <stdlib.h>
@@ -45,18 +52,17 @@ constexpr int G_WARPS = 10;
 constexpr int G_THREADS = 32 * G_WARPS;
 constexpr int EPI_WARPS = 4;
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
-constexpr int MMA_WARPS = 1;                   // one MMA issuer (warp 1).  Several issuers sharing one ring are NOT safe: a warp
-                                               // that skips stages it does not own can be a whole ring lap ahead of a barrier, and a
-                                               // 1-bit phase-parity wait then passes on the previous lap (seen as wrong logits / hangs)
-constexpr int EPI_WARP0 = 1 + MMA_WARPS;       // epilogue warps 2..5: warp % 4 == TMEM lane quarter (any 4 consecutive warps)
-constexpr int G_WARP0 = EPI_WARP0 + EPI_WARPS; // gather warps 6..15
-constexpr int NTHREADS = 32 * G_WARP0 + G_THREADS;         // 512
+constexpr int RINGS = 2;                       // weight rings; one producer warp and one MMA warp per ring
+constexpr int MMA_WARP0 = RINGS;               // producers: warps 0..1, MMA issuers: warps 2..3
+constexpr int EPI_WARP0 = 2 * RINGS;           // epilogue warps 4..7: warp % 4 == TMEM lane quarter
+constexpr int G_WARP0 = EPI_WARP0 + EPI_WARPS; // gather warps 8..17
+constexpr int NTHREADS = 32 * G_WARP0 + G_THREADS;         // 576 (18 warps: 96 registers per thread)
 constexpr int STAGE_BYTES = 128 * 128;         // one weight box: 128 neurons x 64 bf16
-constexpr int MAX_STAGES = 12;
+constexpr int RING_MAX = 6;                    // stages per ring
 constexpr int MAX_L = 4;
 constexpr int MAX_MT = 4;                      // 128-neuron tiles per layer (width <= 512)
 constexpr int MAX_W = 512;
-constexpr int G_ROUNDS = 2;                    // phase-D rounds of the gather group: K <= G_ROUNDS * G_WARPS
+constexpr int G_ROUNDS = 2;                    // phase-D rounds of the gather group (generic shapes): K <= G_ROUNDS * G_WARPS
 constexpr int BAR_GATHER = 1, BAR_EPI = 2;     // named barriers
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
@@ -74,11 +80,11 @@ struct Params {
     float* prob;
     long long B;
     int num_tiles, cluster;
-    int x_chunks;                               // 64-wide K chunks per activation buffer
-    int nstage;
-    uint32_t oX1, oRing, oImg, oPart, oIdx, oXv, oMisc;   // shared-memory offsets from the 1024-aligned base
+    int x_chunks;                               // 64-wide K chunks of the activation buffer
+    int nst[2];                                 // stages of ring 0 / ring 1
+    uint32_t oE, oRing, oImg, oPart, oIdx, oXv, oMisc;   // shared-memory offsets from the 1024-aligned base (X is at 0)
     int* err;
-    long long* clk;                             // optional per-CTA timeline (debug tooling): 32 x int64 per CTA
+    long long* clk;                             // optional per-CTA timeline (debug tooling): FZ_NCLK x int64 per CTA
     volatile int* prog;                         // optional progress markers in pinned host memory (debug): 32 ints per CTA
 };
 #define FZ_PROG(slot, val) do { if (p.prog && lane == 0) p.prog[blockIdx.x * 32 + (slot)] = (val); } while (0)
@@ -108,7 +114,7 @@ constexpr int MAX_U = 1152;                    // usize(47) + 4 = 1108 floats
 struct alignas(16) UParam { int valid; int pad_[3]; float u[MAX_U]; };
 
 struct Bars {
-    uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+    uint64_t full[2][RING_MAX], empty[2][RING_MAX];
     uint64_t x_ready, shallow_ready, tile_done;
     uint64_t act_ready[2][MAX_MT], acc_full[2][MAX_MT];
     uint32_t tmem_holder, pad_;
@@ -116,29 +122,40 @@ struct Bars {
     float red[EPI_WARPS][TS];
 };
 
+struct RingPos {
+    uint32_t s, ph;
+    __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1; } }
+};
+
 // ---------------------------------------------------------------------------------------- the kernel
+// FT/KT > 0: compile-time field count / embedding width (KT <= 10): the fp32 gather block aliases the activation buffer
+// and phase D runs from registers.  FT == 0: generic shapes, separate fp32 block, pair-list second order.
 template <bool SPLIT, int FT, int KT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UParam up, const Params p) {
     constexpr int NB = SPLIT ? 64 : 32;                 // B-operand rows per chunk == accumulator columns per neuron tile
-    constexpr int CH = NB * 128;                        // bytes of one 64-wide K chunk of an activation buffer
+    constexpr int CH = NB * 128;                        // bytes of one 64-wide K chunk of the activation buffer
+    constexpr int H = SPLIT ? 2 : 1;                    // weight boxes per (tile, chunk): hi [, lo]
+    static_assert(KT <= G_WARPS, "the register path owns one embedding column per gather warp pair");
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment: the 128B swizzle is a function of shared-memory address bits [4,10)
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* sX[2] = {base, base + p.oX1};
-    unsigned char* sW = base + p.oRing;
+    unsigned char* sX = base;
+    unsigned char* sW = base + p.oRing;                 // ring 0 stages, then ring 1 stages
     Bars* bars = reinterpret_cast<Bars*>(base + p.oMisc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int L = p.depth, NSTAGE = p.nstage, CL = p.cluster;
+    const int L = p.depth, CL = p.cluster;
+    const uint32_t NS0 = (uint32_t)p.nst[0], NS1 = (uint32_t)p.nst[1];
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1);
     if (p.clk && threadIdx.x == 0) {           // debug timeline: kernel entry in SM clocks and in the global ns timer
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.clk[blockIdx.x * FZ_NCLK + 28] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 29] = (long long)t;
     }
-    const uint16_t cmask = (uint16_t)((1u << CL) - 1);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], CL); }
+        for (int r = 0; r < 2; ++r)
+            for (int s = 0; s < RING_MAX; ++s) { mbar_init(&bars->full[r][s], 1); mbar_init(&bars->empty[r][s], CL); }
         mbar_init(&bars->x_ready, G_THREADS);
         mbar_init(&bars->shallow_ready, G_THREADS);
         mbar_init(&bars->tile_done, EPI_THREADS);
@@ -146,148 +163,165 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
             for (int m = 0; m < MAX_MT; ++m) { mbar_init(&bars->act_ready[b][m], EPI_THREADS); mbar_init(&bars->acc_full[b][m], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int l = 0; l < L; ++l)
-            for (int h = 0; h < (SPLIT ? 2 : 1); ++h) { tma_prefetch_desc(&maps.w[l][h][0]); tma_prefetch_desc(&maps.w[l][h][1]); }
+            for (int h = 0; h < H; ++h) { tma_prefetch_desc(&maps.w[l][h][0]); tma_prefetch_desc(&maps.w[l][h][1]); }
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_holder, 512);
+    if (warp == MMA_WARP0) tmem_alloc(&bars->tmem_holder, 512);
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();    // the peers' barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_holder;
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
-    // every CTA of a cluster runs the same number of tiles (the weight ring is shared); tiles past the end are dummies
+    // every CTA of a cluster runs the same number of tiles (the weight rings are shared); tiles past the end are dummies
     const int n_iter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
     auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
     auto layer_n = [&](int l) { return pad16(p.widths[l]); };
 
-    if (warp == 0) {
-        // ================================================================= TMA producer
-        // The whole warp walks the loop (warp-uniform control flow keeps the address arithmetic on the uniform datapath);
-        // one elected lane issues.
-        uint32_t stage = 0, sphase = 0;
+    if (warp < RINGS) {
+        // ================================================================= TMA producers: warp 0 feeds ring 0 (even neuron tiles),
+        // warp 1 feeds ring 1 (odd tiles).  Issuing a box costs the warp ~250 cycles (probe, expect_tx, TMA issue), so one warp
+        // tops out near 60 B/clk; two keep up with the MMA pipe.  Each ring is filled and drained strictly in order.
+        const int pw = warp;
+        const uint32_t NS = pw ? NS1 : NS0;
+        uint64_t* full = bars->full[pw];
+        uint64_t* empty = bars->empty[pw];
+        unsigned char* ring = sW + (pw ? (size_t)NS0 * STAGE_BYTES : 0);
+        RingPos rp{0, 0};
         for (int it = 0; it < n_iter; ++it) {
             for (int l = 0; l < L; ++l) {
                 const int kch = (layer_k(l) + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad);
-                // neuron-tile-major order: tile mt's accumulators complete while the later tiles are still being multiplied,
-                // so its epilogue overlaps them
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int rows = mtile_rows(npad, mt), per = rows / CL;
-                    const uint32_t dst_off = (uint32_t)(crank * per * 128);
-                    const int row0 = mt * 128 + (int)crank * per;
-                    const uint32_t bytes = (uint32_t)(rows * 128);
-                    const int which = rows == 64 ? 1 : 0;
-                    // two boxes per iteration (hi + lo of one chunk, or two chunks): both empty-barrier probes are issued
-                    // before either is resolved, so the ~100-cycle probe latency is paid once per 32 KB, not per 16 KB
-                    constexpr int CPG = SPLIT ? 1 : 2;              // K chunks per iteration
-                    for (int c = 0; c < kch; c += CPG) {
-                        const bool two = SPLIT || (c + 1 < kch);
-                        const uint32_t s0 = stage, ph0 = sphase;
-                        uint32_t s1 = s0 + 1, ph1 = ph0;
-                        if (s1 == (uint32_t)NSTAGE) { s1 = 0; ph1 ^= 1; }
-                        const bool r0 = mbar_try(&bars->empty[s0], ph0 ^ 1);
-                        const bool r1 = two ? mbar_try(&bars->empty[s1], ph1 ^ 1) : true;
-                        FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | (1 << 24));
-                        if (!r0) mbar_wait(&bars->empty[s0], ph0 ^ 1, p.err, 12);
-                        if (!r1) mbar_wait(&bars->empty[s1], ph1 ^ 1, p.err, 13);
-                        FZ_PROG(0, (l << 16) | (c << 8) | (mt << 4) | (2 << 24));
-                        unsigned char* dst0 = sW + (size_t)s0 * STAGE_BYTES + dst_off;
-                        unsigned char* dst1 = sW + (size_t)s1 * STAGE_BYTES + dst_off;
-                        const CUtensorMap* map0 = &maps.w[l][0][which];
-                        const CUtensorMap* map1 = &maps.w[l][SPLIT ? 1 : 0][which];
-                        const int c1 = SPLIT ? c : c + 1;
+                for (int c = 0; c < kch; ++c) {
+                    for (int t = pw; t < MT; t += RINGS) {
+                        RingPos s0 = rp, s1 = rp;
+                        if (SPLIT) s1.next(NS);
+                        // both probes in flight before either is resolved (~100 cycles each even when the stage is long free)
+                        const bool k0 = mbar_try(&empty[s0.s], s0.ph ^ 1);
+                        const bool k1 = SPLIT ? mbar_try(&empty[s1.s], s1.ph ^ 1) : true;
+                        FZ_PROG(pw, (l << 16) | (c << 8) | (t << 4) | (1 << 24));
+                        if (!k0) mbar_wait(&empty[s0.s], s0.ph ^ 1, p.err, 12);
+                        if (!k1) mbar_wait(&empty[s1.s], s1.ph ^ 1, p.err, 13);
+                        FZ_PROG(pw, (l << 16) | (c << 8) | (t << 4) | (2 << 24));
+                        const int rows = mtile_rows(npad, t), per = rows / CL;
+                        unsigned char* d0 = ring + (size_t)s0.s * STAGE_BYTES + (size_t)crank * per * 128;
+                        unsigned char* d1 = ring + (size_t)s1.s * STAGE_BYTES + (size_t)crank * per * 128;
+                        const int row0 = t * 128 + (int)crank * per, which = rows == 64 ? 1 : 0;
+                        const uint32_t bytes = (uint32_t)(rows * 128);
                         if (elect_one()) {
-                            mbar_expect_tx(&bars->full[s0], bytes);
-                            if (CL > 1) tma_load_2d_mc(dst0, map0, &bars->full[s0], c * KCH, row0, cmask);
-                            else tma_load_2d(dst0, map0, &bars->full[s0], c * KCH, row0);
-                            if (two) {
-                                mbar_expect_tx(&bars->full[s1], bytes);
-                                if (CL > 1) tma_load_2d_mc(dst1, map1, &bars->full[s1], c1 * KCH, row0, cmask);
-                                else tma_load_2d(dst1, map1, &bars->full[s1], c1 * KCH, row0);
+                            mbar_expect_tx(&full[s0.s], bytes);
+                            if (CL > 1) tma_load_2d_mc(d0, &maps.w[l][0][which], &full[s0.s], c * KCH, row0, cmask);
+                            else tma_load_2d(d0, &maps.w[l][0][which], &full[s0.s], c * KCH, row0);
+                            if (SPLIT) {
+                                mbar_expect_tx(&full[s1.s], bytes);
+                                if (CL > 1) tma_load_2d_mc(d1, &maps.w[l][1][which], &full[s1.s], c * KCH, row0, cmask);
+                                else tma_load_2d(d1, &maps.w[l][1][which], &full[s1.s], c * KCH, row0);
                             }
                         }
                         __syncwarp();
-                        stage = s1; sphase = ph1;
-                        if (two) { if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; } }
+                        rp = s1; rp.next(NS);
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================================================= MMA issuer
-        // Whole warp in the loop, one elected lane issues: descriptors stay in uniform registers (a lane-0 branch costs ~35
-        // dependent instructions = 160 cycles per tcgen05.mma, 10x the N = 32 floor).
-        uint32_t stage = 0, sphase = 0;
+    } else if (warp < EPI_WARP0) {
+        // ================================================================= MMA issuers: warp 2 = ring 0 (even tiles), warp 3 = ring 1
+        const int mw = warp - MMA_WARP0;
+        const uint32_t NS = mw ? NS1 : NS0;
+        uint64_t* full = bars->full[mw];
+        uint64_t* empty = bars->empty[mw];
+        const uint32_t sW_u32 = smem_u32(sW) + (mw ? NS0 * (uint32_t)STAGE_BYTES : 0u);
+        const uint32_t sX_u32 = smem_u32(sX);
+        RingPos rp{0, 0};
         uint32_t act_bits = 0;                       // phase parity of act_ready[buf][g], bit buf * MAX_MT + g
-        const uint32_t sW_u32 = smem_u32(sW);
-        const uint32_t sX0_u32 = smem_u32(sX[0]), sX1_u32 = smem_u32(sX[1]);
         for (int it = 0; it < n_iter; ++it) {
-            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 20);   // TMEM drained, X buffers free
+            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 20);   // TMEM drained, X free
             for (int l = 0; l < L; ++l) {
                 const int buf = l & 1;
                 const int K = layer_k(l), kch = (K + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad);
-                const uint32_t sXb = buf ? sX1_u32 : sX0_u32;
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int rows = mtile_rows(npad, mt);
-                    const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + mt * NB);
-                    const uint32_t idesc = make_idesc(rows, NB), idesc_lo = make_idesc(rows, 32);
-                    constexpr int CPG = SPLIT ? 1 : 2;              // K chunks per iteration (two ring stages either way)
-                    for (int c = 0; c < kch; c += CPG) {
-                        if (mt == 0) {
-                            if (l == 0) {
-                                if (c == 0) { if (it == 0 && lane == 0) FZ_CLK(0); mbar_wait(&bars->x_ready, (uint32_t)(it & 1), p.err, 21); if (it == 0 && lane == 0) FZ_CLK(1); }
-                            } else if ((c & 1) == 0) {
-                                // chunks c, c+1 hold neurons [64c, 64c+128) of the previous layer = its neuron tile c/2
-                                const int g = c >> 1, bit = buf * MAX_MT + g;
-                                FZ_PROG(1, (l << 16) | (c << 8) | (5 << 24));
-                                mbar_wait(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
-                                act_bits ^= 1u << bit;
+                const bool active = mw < MT;          // a one-tile layer puts nothing into ring 1; its barriers are still observed
+                const int tA = mw, tB = mw + 2;
+                const bool hasB = tB < MT;
+                const int rowsA = mtile_rows(npad, tA), rowsB = hasB ? mtile_rows(npad, tB) : 128;
+                const uint32_t dA = tmem_base + (uint32_t)(buf * 256 + tA * NB), dB = tmem_base + (uint32_t)(buf * 256 + tB * NB);
+                const uint32_t idA = make_idesc(rowsA, NB), idB = make_idesc(rowsB, NB);
+                const uint32_t idAlo = make_idesc(rowsA, 32), idBlo = make_idesc(rowsB, 32);
+                for (int c = 0; c < kch; ++c) {
+                    if (l == 0) {
+                        if (c == 0) { if (it == 0 && lane == 0 && mw == 0) FZ_CLK(0); mbar_wait(&bars->x_ready, (uint32_t)(it & 1), p.err, 21); if (it == 0 && lane == 0 && mw == 0) FZ_CLK(1); }
+                    } else if ((c & 1) == 0) {
+                        // chunks c, c+1 hold neurons [64c, 64c+128) of the previous layer = its neuron tile c/2
+                        const int g = c >> 1, bit = buf * MAX_MT + g;
+                        FZ_PROG(2 + mw, (l << 16) | (c << 8) | (5 << 24));
+                        mbar_wait(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
+                        act_bits ^= 1u << bit;
+                    }
+                    if (!active) continue;
+                    const int ks = min(4, (K - c * KCH) / 16);
+                    const uint64_t bdesc = make_desc_sw128(sX_u32 + (uint32_t)(c * CH));
+                    const uint32_t acc0 = c ? 1u : 0u;
+                    const bool last_c = c == kch - 1;
+                    if constexpr (SPLIT) {
+                        // one iteration per tile: its hi and lo boxes (two stages, probes overlapped), 2 * ks MMAs
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (j == 1 && !hasB) break;
+                            const uint32_t dcol = j ? dB : dA, idh = j ? idB : idA, idl = j ? idBlo : idAlo;
+                            RingPos s0 = rp, s1 = rp; s1.next(NS);
+                            const bool k0 = mbar_try(&full[s0.s], s0.ph), k1 = mbar_try(&full[s1.s], s1.ph);
+                            FZ_PROG(2 + mw, (l << 16) | (c << 8) | ((j ? tB : tA) << 4) | (3 << 24));
+                            if (!k0) mbar_wait(&full[s0.s], s0.ph, p.err, 24);
+                            if (!k1) mbar_wait(&full[s1.s], s1.ph, p.err, 25);
+                            tc_fence_after();
+                            const uint64_t ah = make_desc_sw128(sW_u32 + s0.s * (uint32_t)STAGE_BYTES);
+                            const uint64_t al = make_desc_sw128(sW_u32 + s1.s * (uint32_t)STAGE_BYTES);
+                            if (elect_one()) {
+                                umma_bf16(dcol, ah, bdesc, idh, acc0);                     // +32 bytes (16 bf16) along K per step
+                                if (ks > 1) umma_bf16(dcol, ah + 2, bdesc + 2, idh, 1u);
+                                if (ks > 2) umma_bf16(dcol, ah + 4, bdesc + 4, idh, 1u);
+                                if (ks > 3) umma_bf16(dcol, ah + 6, bdesc + 6, idh, 1u);
+                                if (CL > 1) umma_commit_mc(&empty[s0.s], cmask); else umma_commit(&empty[s0.s]);
+                                umma_bf16(dcol, al, bdesc, idl, 1u);
+                                if (ks > 1) umma_bf16(dcol, al + 2, bdesc + 2, idl, 1u);
+                                if (ks > 2) umma_bf16(dcol, al + 4, bdesc + 4, idl, 1u);
+                                if (ks > 3) umma_bf16(dcol, al + 6, bdesc + 6, idl, 1u);
+                                if (CL > 1) umma_commit_mc(&empty[s1.s], cmask); else umma_commit(&empty[s1.s]);
+                                if (last_c) umma_commit(&bars->acc_full[buf][j ? tB : tA]);   // accumulators of (layer l, tile) complete
                             }
+                            __syncwarp();
+                            rp = s1; rp.next(NS);
                         }
-                        const bool two = SPLIT || (c + 1 < kch);
-                        const int c1 = SPLIT ? c : c + 1;
-                        const int ks0 = min(4, (K - c * KCH) / 16), ks1 = two ? min(4, (K - c1 * KCH) / 16) : 0;
-                        const uint64_t bdesc0 = make_desc_sw128(sXb + (uint32_t)(c * CH));
-                        const uint64_t bdesc1 = make_desc_sw128(sXb + (uint32_t)(c1 * CH));
-                        const uint32_t s0 = stage, ph0 = sphase;
-                        uint32_t s1 = s0 + 1, ph1 = ph0;
-                        if (s1 == (uint32_t)NSTAGE) { s1 = 0; ph1 ^= 1; }
-                        // both probes in flight together; the blocking waits only run when the weights have not landed yet
-                        const bool r0 = mbar_try(&bars->full[s0], ph0);
-                        const bool r1 = two ? mbar_try(&bars->full[s1], ph1) : true;
-                        FZ_PROG(1, (l << 16) | (c << 8) | (mt << 4) | (3 << 24));
-                        if (!r0) mbar_wait(&bars->full[s0], ph0, p.err, 24);
-                        if (!r1) mbar_wait(&bars->full[s1], ph1, p.err, 25);
+                    } else {
+                        // one iteration per chunk: this ring's (up to) two tiles, one box each
+                        RingPos s0 = rp, s1 = rp; s1.next(NS);
+                        const bool k0 = mbar_try(&full[s0.s], s0.ph), k1 = hasB ? mbar_try(&full[s1.s], s1.ph) : true;
+                        FZ_PROG(2 + mw, (l << 16) | (c << 8) | (tA << 4) | (3 << 24));
+                        if (!k0) mbar_wait(&full[s0.s], s0.ph, p.err, 24);
+                        if (!k1) mbar_wait(&full[s1.s], s1.ph, p.err, 25);
                         tc_fence_after();
-                        const uint64_t adesc0 = make_desc_sw128(sW_u32 + s0 * (uint32_t)STAGE_BYTES);
-                        const uint64_t adesc1 = make_desc_sw128(sW_u32 + s1 * (uint32_t)STAGE_BYTES);
-                        const uint32_t id1 = SPLIT ? idesc_lo : idesc;
-                        const uint32_t acc0 = c ? 1u : 0u;
-                        const bool last_c = c1 == kch - 1 || c == kch - 1;
+                        const uint64_t a0 = make_desc_sw128(sW_u32 + s0.s * (uint32_t)STAGE_BYTES);
+                        const uint64_t a1 = make_desc_sw128(sW_u32 + s1.s * (uint32_t)STAGE_BYTES);
                         if (elect_one()) {
-                            umma_bf16(dcol, adesc0, bdesc0, idesc, acc0);                  // +32 bytes (16 bf16) along K per step
-                            if (ks0 > 1) umma_bf16(dcol, adesc0 + 2, bdesc0 + 2, idesc, 1u);
-                            if (ks0 > 2) umma_bf16(dcol, adesc0 + 4, bdesc0 + 4, idesc, 1u);
-                            if (ks0 > 3) umma_bf16(dcol, adesc0 + 6, bdesc0 + 6, idesc, 1u);
-                            if (CL > 1) umma_commit_mc(&bars->empty[s0], cmask);           // this CTA is done with the stage (all CTAs are told)
-                            else umma_commit(&bars->empty[s0]);
-                            if (two) {
-                                umma_bf16(dcol, adesc1, bdesc1, id1, 1u);
-                                if (ks1 > 1) umma_bf16(dcol, adesc1 + 2, bdesc1 + 2, id1, 1u);
-                                if (ks1 > 2) umma_bf16(dcol, adesc1 + 4, bdesc1 + 4, id1, 1u);
-                                if (ks1 > 3) umma_bf16(dcol, adesc1 + 6, bdesc1 + 6, id1, 1u);
-                                if (CL > 1) umma_commit_mc(&bars->empty[s1], cmask);
-                                else umma_commit(&bars->empty[s1]);
+                            umma_bf16(dA, a0, bdesc, idA, acc0);
+                            if (ks > 1) umma_bf16(dA, a0 + 2, bdesc + 2, idA, 1u);
+                            if (ks > 2) umma_bf16(dA, a0 + 4, bdesc + 4, idA, 1u);
+                            if (ks > 3) umma_bf16(dA, a0 + 6, bdesc + 6, idA, 1u);
+                            if (CL > 1) umma_commit_mc(&empty[s0.s], cmask); else umma_commit(&empty[s0.s]);
+                            if (last_c) umma_commit(&bars->acc_full[buf][tA]);
+                            if (hasB) {
+                                umma_bf16(dB, a1, bdesc, idB, acc0);
+                                if (ks > 1) umma_bf16(dB, a1 + 2, bdesc + 2, idB, 1u);
+                                if (ks > 2) umma_bf16(dB, a1 + 4, bdesc + 4, idB, 1u);
+                                if (ks > 3) umma_bf16(dB, a1 + 6, bdesc + 6, idB, 1u);
+                                if (CL > 1) umma_commit_mc(&empty[s1.s], cmask); else umma_commit(&empty[s1.s]);
+                                if (last_c) umma_commit(&bars->acc_full[buf][tB]);
                             }
-                            // accumulators of (layer l, neuron tile mt) complete after the last chunk
-                            if (last_c) umma_commit(&bars->acc_full[buf][mt]);
                         }
                         __syncwarp();
-                        stage = s1; sphase = ph1;
-                        if (two) { if (++stage == (uint32_t)NSTAGE) { stage = 0; sphase ^= 1; } }
+                        rp = s0; rp.next(NS);
+                        if (hasB) rp.next(NS);
                     }
-                    if (it == 0 && l < 4 && mt == MT - 1 && lane == 0) FZ_CLK(2 + l);
                 }
+                if (it == 0 && l < 4 && lane == 0 && mw == 0) FZ_CLK(2 + l);
             }
         }
     } else if (warp < G_WARP0) {
@@ -303,15 +337,20 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
             for (int l = 0; l < L; ++l) {
                 const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad);
                 const bool last = (l == L - 1);
-                unsigned char* xn = sX[(l + 1) & 1];
                 for (int mt = 0; mt < MT; ++mt) {
-                    FZ_PROG(8 + ewarp, (l << 16) | (mt << 4) | (6 << 24));
-                    mbar_wait(&bars->acc_full[buf][mt], (acc_bits >> (buf * MAX_MT + mt)) & 1u, p.err, 31);
+                    // The output of tile mt overwrites chunks 2mt, 2mt+1 of the SAME activation buffer the layer reads, so every
+                    // MMA reading them must have finished: both issuers interleave their tiles chunk by chunk, hence once the first
+                    // tile of each ring (0 and 1) is complete all chunks but the last are dead; the last chunk is written by the
+                    // last tile, by which time every acc_full of the layer has been waited for.
+                    const int nwait = (mt == 0 && MT > 1) ? 2 : (mt == 1 ? 0 : 1);
+                    for (int w = 0; w < nwait; ++w) {
+                        const int t = mt + w, bit = buf * MAX_MT + t;
+                        FZ_PROG(8 + ewarp, (l << 16) | (t << 4) | (6 << 24));
+                        mbar_wait(&bars->acc_full[buf][t], (acc_bits >> bit) & 1u, p.err, 31);
+                        acc_bits ^= 1u << bit;
+                    }
                     FZ_PROG(8 + ewarp, (l << 16) | (mt << 4) | (7 << 24));
-                    acc_bits ^= 1u << (buf * MAX_MT + mt);
                     if (threadIdx.x == 32 * EPI_WARP0 && it == 0 && l < 4 && mt == 0) FZ_CLK(8 + 2 * l);
-                    // layer 1's output goes to X1, which aliases the fp32 gather block: the FwFM warps must be done reading it
-                    if (l == 0 && mt == 0 && !last) mbar_wait(&bars->shallow_ready, (uint32_t)(it & 1), p.err, 32);
                     tc_fence_after();
                     const int n = mt * 128 + row;
                     const int rows_valid = min(128, npad - mt * 128);   // neurons [N, npad) are zero rows: they write the K padding
@@ -340,31 +379,29 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                             for (int s = 0; s < TS; ++s) v[s] = fmaxf(v[s] + bb, 0.f) * ff;
 #pragma unroll
                             for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
-                                const bool up = (lane & off) != 0;
+                                const bool upper = (lane & off) != 0;
 #pragma unroll
                                 for (int i = 0; i < nn / 2; ++i) {
-                                    const float send = up ? v[i] : v[i + nn / 2];
-                                    const float keep = up ? v[i + nn / 2] : v[i];
+                                    const float send = upper ? v[i] : v[i + nn / 2];
+                                    const float keep = upper ? v[i + nn / 2] : v[i];
                                     v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                                 }
                             }
                             zsum += v[0];
                         } else if (row < rows_valid) {
                             const float bb = n < N ? __ldg(p.bias[l] + n) : 0.f;
-                            {
-                                // element (sample s, k = n) of the next operand: chunk n/64, row s (hi) / 32+s (lo), 16-byte unit
-                                // ((n%64)/8) ^ (row%8), byte (n%8)*2
-                                unsigned char* xc = xn + (size_t)(n >> 6) * CH + (n & 7) * 2;
-                                const int u = (n & 63) >> 3;
+                            // element (sample s, k = n) of the next operand: chunk n/64, row s (hi) / 32+s (lo), 16-byte unit
+                            // ((n%64)/8) ^ (row%8), byte (n%8)*2
+                            unsigned char* xc = sX + (size_t)(n >> 6) * CH + (n & 7) * 2;
+                            const int u = (n & 63) >> 3;
 #pragma unroll
-                                for (int s = 0; s < TS; ++s) {
-                                    const float a = fmaxf(v[s] + bb, 0.f);
-                                    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-                                    unsigned char* dst = xc + s * 128 + ((u ^ (s & 7)) << 4);
-                                    *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-                                    if constexpr (SPLIT)
-                                        *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(a - __bfloat162float(hi));
-                                }
+                            for (int s = 0; s < TS; ++s) {
+                                const float a = fmaxf(v[s] + bb, 0.f);
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+                                unsigned char* dst = xc + s * 128 + ((u ^ (s & 7)) << 4);
+                                *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                                if constexpr (SPLIT)
+                                    *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(a - __bfloat162float(hi));
                             }
                         }
                     }
@@ -397,70 +434,166 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         // ================================================================= gather group
         const int gtid = threadIdx.x - 32 * G_WARP0;
         const int F = FT > 0 ? FT : p.ep.F, K = KT > 0 ? KT : p.ep.K;
-        const int FK = F * K;
+        const int FK = F * K, Kp = pad16(FK);
         TileSmem sm;
         sm.img = base + p.oImg;
-        sm.E = reinterpret_cast<float*>(sX[1]);         // the fp32 block aliases X1 (free until layer 1's epilogue)
+        sm.E = reinterpret_cast<float*>(base + p.oE);    // FT > 0: aliases the activation buffer
         sm.part = reinterpret_cast<float*>(base + p.oPart);
         sm.idx = reinterpret_cast<int32_t*>(base + p.oIdx);
         sm.xv = reinterpret_cast<float*>(base + p.oXv);
         sm.EP = e_pitch(FK);
-        const int units = pad16(FK) >> 3;               // 16-byte (8 x bf16) units per operand row
         for (int it = 0; it < n_iter; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int64_t b0 = (int64_t)tile * TS;
             int64_t left = p.ep.B - b0;
             const int nrows = (int)(left < 0 ? 0 : (left > TS ? TS : left));
-            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 40);      // X1 (= the fp32 block) is free again
+            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 40);      // the previous tile is done with X
             float first_acc[G_ROUNDS];
             long long* gclk = (p.clk && it == 0) ? p.clk + blockIdx.x * FZ_NCLK + 96 : nullptr;
             embed_gather<FT, KT, TS, G_ROUNDS, BAR_GATHER>(p.ep, sm, base + p.oImg, it == 0, gtid, G_THREADS, b0, nrows, first_acc, gclk);
             if (gtid == 0 && it == 0) FZ_CLK(20);
-            // fp32 block -> bf16 (hi | lo) operand of layer 1: X0[s][k], K-major, 128B swizzle; columns >= F*K are zero
-            for (int i = gtid; i < TS * units; i += G_THREADS) {
-                const int s = i / units, u8 = i - s * units;
-                const float* src = sm.E + s * sm.EP + 8 * u8;
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c0 = 8 * u8 + 2 * j;
-                    float2 t = make_float2(0.f, 0.f);
-                    if (c0 + 1 < FK) t = *reinterpret_cast<const float2*>(src + 2 * j);
-                    else if (c0 < FK) t.x = src[2 * j];
-                    x[2 * j] = t.x; x[2 * j + 1] = t.y;
+            if constexpr (FT > 0) {
+                // ---- register path: this thread owns (sample smp, column kk); its F values leave the fp32 block for registers,
+                // the block is then overwritten in place by the bf16 (hi | lo) operand of layer 1, and the interaction runs from
+                // the registers while the tensor cores start.  A pruned field matrix (pair list) is walked before the overwrite.
+                constexpr int FTc = FT > 0 ? FT : 1, KTc = KT > 0 ? KT : 1;
+                const ImgLayout IL = img_layout(FTc, KTc);
+                const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sm.img + IL.oHdr);
+                const PairEnt* sPairs = reinterpret_cast<const PairEnt*>(sm.img + IL.oPairs);
+                const float* sWl = reinterpret_cast<const float*>(sm.img + IL.oWl);
+                const int smp = owner_sample<TS>(gtid), kk = owner_col<TS>(gtid, G_THREADS, 0);
+                const bool owner = kk < KTc;
+                const bool use_list = (hdr->live * 6 < FTc * (FTc - 1) / 2) || !up.valid;
+                const float* myE = sm.E + smp * sm.EP + (owner ? kk : 0);
+                float second = 0.f;
+                if (use_list && owner) {
+                    const int n = hdr->n_list;
+                    float s0 = 0.f, s1 = 0.f;
+                    int q = 0;
+#pragma unroll 1
+                    for (; q + 1 < n; q += 2) {
+                        const PairEnt a = sPairs[q], b = sPairs[q + 1];
+                        s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
+                        s1 = fmaf(b.u * myE[b.ij & 0xffffu], myE[b.ij >> 16], s1);
+                    }
+                    if (q < n) {
+                        const PairEnt a = sPairs[q];
+                        s0 = fmaf(a.u * myE[a.ij & 0xffffu], myE[a.ij >> 16], s0);
+                    }
+                    second = s0 + s1;
                 }
-                uint4 hi4, lo4;
-                uint32_t* hp = reinterpret_cast<uint32_t*>(&hi4);
-                uint32_t* lp = reinterpret_cast<uint32_t*>(&lo4);
+                float e[FTc];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
-                    hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                    if constexpr (SPLIT) {
-                        const float2 hf = __bfloat1622float2(h2);
-                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
-                        lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                for (int f = 0; f < FTc; ++f) e[f] = owner ? myE[f * KTc] : 0.f;
+                group_sync<BAR_GATHER>(G_THREADS);          // every thread holds its values: the block may be overwritten
+                if (owner) {
+#pragma unroll
+                    for (int f = 0; f < FTc; ++f) {
+                        const int col = f * KTc + kk;       // element (sample smp, k = col): chunk col/64, 16-byte unit, byte (col%8)*2
+                        unsigned char* dst = sX + (size_t)(col >> 6) * CH + smp * 128 + ((((col & 63) >> 3) ^ (smp & 7)) << 4) + (col & 7) * 2;
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(e[f]);
+                        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                        if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
                     }
                 }
-                unsigned char* dst = sX[0] + (size_t)(u8 >> 3) * CH + s * 128 + (((u8 & 7) ^ (s & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = hi4;
-                if constexpr (SPLIT) *reinterpret_cast<uint4*>(dst + 32 * 128) = lo4;
+                for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
+                    const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
+                    unsigned char* dst = sX + (size_t)(col >> 6) * CH + s * 128 + ((((col & 63) >> 3) ^ (s & 7)) << 4) + (col & 7) * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
+                    if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(0.f);
+                }
+                fence_async_smem();
+                mbar_arrive(&bars->x_ready);
+                if (gtid == 0 && it == 0) FZ_CLK(21);
+                if (gclk && gtid == 0) gclk[5] = clock64();
+                if (owner) {
+                    float acc = first_acc[0];
+                    if (p.ep.flags & DFW_USE_FWLW) {          // model/DeepFMs.py:344-345
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int f = 0; f < FTc; ++f) {
+                            if (f & 1) a1 = fmaf(e[f], sWl[f * KTc + kk], a1); else a0 = fmaf(e[f], sWl[f * KTc + kk], a0);
+                        }
+                        acc = a0 + a1;
+                    }
+                    if (!use_list) {
+                        // second = sum_j e_j * (sum_{i<j} U_ij e_i): every U_ij is a constant-bank operand, 4 independent chains per j
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int j = 1; j < FTc; ++j) {
+                            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < j; ++i) {
+                                const float u = up.u[ucol_off(j) + i];
+                                if ((i & 3) == 0) d0 = fmaf(u, e[i], d0);
+                                else if ((i & 3) == 1) d1 = fmaf(u, e[i], d1);
+                                else if ((i & 3) == 2) d2 = fmaf(u, e[i], d2);
+                                else d3 = fmaf(u, e[i], d3);
+                            }
+                            const float dot = (d0 + d1) + (d2 + d3);
+                            if (j & 1) s0 = fmaf(e[j], dot, s0); else s1 = fmaf(e[j], dot, s1);
+                        }
+                        second = s0 + s1;
+                    }
+                    sm.part[kk * TS + smp] = acc + second;
+                }
+                group_sync<BAR_GATHER>(G_THREADS);
+                if (gclk && gtid == 0) gclk[6] = clock64();
+                if (gtid < nrows) {                             // fixed-order reduction over k
+                    float tot = 0.f;
+#pragma unroll 1
+                    for (int k = 0; k < KTc; ++k) tot += sm.part[k * TS + gtid];
+                    bars->shallow[gtid] = tot + __ldg(p.ep.bias);
+                }
+                mbar_arrive(&bars->shallow_ready);
+                if (gtid == 0 && it == 0) FZ_CLK(22);
+            } else {
+                // ---- generic shapes: separate fp32 block -> bf16 (hi | lo) operand of layer 1, then the pair-list interaction
+                const int units = Kp >> 3;                  // 16-byte (8 x bf16) units per operand row
+                for (int i = gtid; i < TS * units; i += G_THREADS) {
+                    const int s = i / units, u8 = i - s * units;
+                    const float* src = sm.E + s * sm.EP + 8 * u8;
+                    float x[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c0 = 8 * u8 + 2 * j;
+                        float2 t = make_float2(0.f, 0.f);
+                        if (c0 + 1 < FK) t = *reinterpret_cast<const float2*>(src + 2 * j);
+                        else if (c0 < FK) t.x = src[2 * j];
+                        x[2 * j] = t.x; x[2 * j + 1] = t.y;
+                    }
+                    uint4 hi4, lo4;
+                    uint32_t* hp = reinterpret_cast<uint32_t*>(&hi4);
+                    uint32_t* lp = reinterpret_cast<uint32_t*>(&lo4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+                        hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                        if constexpr (SPLIT) {
+                            const float2 hf = __bfloat1622float2(h2);
+                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+                            lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                    }
+                    unsigned char* dst = sX + (size_t)(u8 >> 3) * CH + s * 128 + (((u8 & 7) ^ (s & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = hi4;
+                    if constexpr (SPLIT) *reinterpret_cast<uint4*>(dst + 32 * 128) = lo4;
+                }
+                fence_async_smem();
+                mbar_arrive(&bars->x_ready);
+                if (gtid == 0 && it == 0) FZ_CLK(21);
+                embed_interact<FT, KT, TS, G_ROUNDS, BAR_GATHER, true>(p.ep, sm, gtid, G_THREADS, nrows, first_acc, bars->shallow, gclk, nullptr);
+                mbar_arrive(&bars->shallow_ready);
+                if (gtid == 0 && it == 0) FZ_CLK(22);
             }
-            fence_async_smem();
-            mbar_arrive(&bars->x_ready);
-            if (gtid == 0 && it == 0) FZ_CLK(21);
-            embed_interact<FT, KT, TS, G_ROUNDS, BAR_GATHER, true>(p.ep, sm, gtid, G_THREADS, nrows, first_acc, bars->shallow, gclk,
-                                                             up.valid ? up.u : nullptr);
-            mbar_arrive(&bars->shallow_ready);
-            if (gtid == 0 && it == 0) FZ_CLK(22);
         }
     }
 
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();    // no CTA exits while a peer may still multicast into it
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
-    if (p.clk && threadIdx.x == 32) {
+    if (warp == MMA_WARP0) tmem_dealloc(tmem_base, 512);
+    if (p.clk && threadIdx.x == 32 * MMA_WARP0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.clk[blockIdx.x * FZ_NCLK + 30] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 31] = (long long)t;
     }
@@ -489,6 +622,9 @@ struct Plan {
     size_t smem_bytes;
 };
 
+// shapes with a compiled register path (the dataset shapes BASELINE.json names)
+static bool specialised(int F, int K) { return K == 10 && (F == 39 || F == 47); }
+
 // Shared-memory plan; returns false (with `why`) when the shapes do not fit the fused form.
 static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why) {
     const int F = m->field_size, K = m->embedding_size, num = m->numerical, FK = F * K;
@@ -504,25 +640,31 @@ static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why
         if (l + 1 < m->depth && pad16(m->widths[l]) > kmax) kmax = pad16(m->widths[l]);
     }
     Params& p = pl.p;
+    const bool alias = specialised(F, K);          // the register path: the fp32 gather block lives inside the activation buffer
     const int NB = split ? 64 : 32, CH = NB * 128;
     p.x_chunks = (kmax + KCH - 1) / KCH;
     const TileSizes ts = tile_sizes(F, K, num, TS);
-    size_t x0 = (size_t)p.x_chunks * CH;
-    size_t x1 = x0 > ts.bE ? x0 : ts.bE;
-    x1 = (x1 + 1023) / 1024 * 1024;
-    size_t o = 0;
-    o += x0;                       p.oX1 = (uint32_t)o;
-    o += x1;                       p.oRing = (uint32_t)o;
+    size_t x = (size_t)p.x_chunks * CH;
+    if (alias && ts.bE > x) x = ts.bE;
+    x = (x + 1023) / 1024 * 1024;
+    size_t o = x;
+    p.oE = 0;
+    if (!alias) { p.oE = (uint32_t)o; o += (ts.bE + 1023) / 1024 * 1024; }
+    p.oRing = (uint32_t)o;
     const size_t tail = up16(img_layout(F, K).total) + ts.bPart + ts.bIdx + ts.bXv + up16(sizeof(Bars)) + 64;
-    if (o + tail + 1024 + 4 * (size_t)STAGE_BYTES > SMEM_LIMIT) { *why = "shared memory: fewer than 4 weight stages fit"; return false; }
-    int nstage = (int)((SMEM_LIMIT - 1024 - o - tail) / STAGE_BYTES);
-    if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-    p.nstage = nstage;
-    o += (size_t)nstage * STAGE_BYTES;   p.oImg = (uint32_t)o;
-    o += up16(img_layout(F, K).total);   p.oPart = (uint32_t)o;
-    o += ts.bPart;                       p.oIdx = (uint32_t)o;
-    o += ts.bIdx;                        p.oXv = (uint32_t)o;
-    o += ts.bXv;                         p.oMisc = (uint32_t)((o + 15) & ~size_t(15));
+    // two rings; a SPLIT iteration takes 2 stages of a ring (hi + lo box), so its rings hold an even number of stages
+    const int min_ring = 2;
+    if (o + tail + 1024 + 2 * (size_t)min_ring * STAGE_BYTES > SMEM_LIMIT) { *why = "shared memory: the two weight rings do not fit"; return false; }
+    int total = (int)((SMEM_LIMIT - 1024 - o - tail) / STAGE_BYTES);
+    if (total > 2 * RING_MAX) total = 2 * RING_MAX;
+    int n0 = (total + 1) / 2, n1 = total / 2;
+    if (split) { n0 &= ~1; n1 &= ~1; }
+    p.nst[0] = n0; p.nst[1] = n1;
+    o += (size_t)(n0 + n1) * STAGE_BYTES; p.oImg = (uint32_t)o;
+    o += up16(img_layout(F, K).total);    p.oPart = (uint32_t)o;
+    o += ts.bPart;                        p.oIdx = (uint32_t)o;
+    o += ts.bIdx;                         p.oXv = (uint32_t)o;
+    o += ts.bXv;                          p.oMisc = (uint32_t)((o + 15) & ~size_t(15));
     o = p.oMisc + sizeof(Bars);
     pl.smem_bytes = o + 1024;
     return true;
@@ -651,8 +793,8 @@ static int run(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st) {
     }
     p.cluster = best_cl;
     {   // debug knobs
-        static const int cap = env_int("DFW_FUSED_STAGES", 0);
-        if (cap >= 2 && cap < p.nstage) p.nstage = cap;
+        static const int cap = env_int("DFW_FUSED_STAGES", 0);      // stages per ring
+        if (cap >= 2) { if (cap < p.nst[0]) p.nst[0] = cap; if (cap < p.nst[1]) p.nst[1] = cap; }
     }
     if (int rc = get_maps(m, SPLIT, best_cl, p.in_dim, maps)) return rc;
     return launch<SPLIT, FT, KT>(maps, pl, best_grid, st);
