@@ -17,7 +17,8 @@
 //                 uniform registers).  K-outer order: chunk c of every tile, then chunk c+1, so the two warps' barrier
 //                 probes / commits (a few hundred cycles per stage) hide behind each other's MMAs.  One ring per warp keeps
 //                 every barrier's phases observed in order (1-bit parity waits are only safe that way).
-//     warps 4-7   epilogue: thread = one neuron (TMEM lane); tcgen05.ld its 32 samples, + bias, ReLU, -> bf16 (hi | lo) into
+//     warps 4-7   epilogue (samples 0..15; gather warps 8-11 take samples 16..31 once their tile's interaction is done):
+//                 thread = one neuron (TMEM lane); tcgen05.ld its samples, + bias, ReLU, -> bf16 (hi | lo) into
 //                 the activation buffer (K-major, 128B swizzle) for the next layer; last layer: x net_1_fc, warp
 //                 transpose-reduction, + shallow, optional sigmoid -> global
 //     warps 8-17  gather group (embed_device.cuh): indices -> rows (cp.async) -> fix-ups (fp32 block in shared memory);
@@ -63,7 +64,8 @@ constexpr int MAX_L = 4;
 constexpr int MAX_MT = 4;                      // 128-neuron tiles per layer (width <= 512)
 constexpr int MAX_W = 512;
 constexpr int G_ROUNDS = 2;                    // phase-D rounds of the gather group (generic shapes): K <= G_ROUNDS * G_WARPS
-constexpr int BAR_GATHER = 1, BAR_EPI = 2;     // named barriers
+constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_INIT = 3, BAR_CORE = 4;     // named barriers
+constexpr int MAX_KCH = 8;                     // 64-wide K chunks of the widest operand (512)
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 struct alignas(64) Maps {
@@ -115,11 +117,11 @@ struct alignas(16) UParam { int valid; int pad_[3]; float u[MAX_U]; };
 
 struct Bars {
     uint64_t full[2][RING_MAX], empty[2][RING_MAX];
-    uint64_t x_ready, shallow_ready, tile_done;
+    uint64_t x_ready[MAX_KCH], shallow_ready, tile_done;
     uint64_t act_ready[2][MAX_MT], acc_full[2][MAX_MT];
     uint32_t tmem_holder, pad_;
     float shallow[TS];
-    float red[EPI_WARPS][TS];
+    float red[2 * EPI_WARPS][16];                 // [sample half * 4 + lane quarter][sample % 16]
 };
 
 struct RingPos {
@@ -156,27 +158,132 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int r = 0; r < 2; ++r)
             for (int s = 0; s < RING_MAX; ++s) { mbar_init(&bars->full[r][s], 1); mbar_init(&bars->empty[r][s], CL); }
-        mbar_init(&bars->x_ready, G_THREADS);
-        mbar_init(&bars->shallow_ready, G_THREADS);
-        mbar_init(&bars->tile_done, EPI_THREADS);
+        // producers of these barriers arrive once per WARP (fence, __syncwarp, lane 0): hundreds of arrives on one mbarrier serialise
+        for (int c = 0; c < MAX_KCH; ++c) mbar_init(&bars->x_ready[c], G_WARPS);
+        mbar_init(&bars->shallow_ready, G_WARPS);
+        mbar_init(&bars->tile_done, 2 * EPI_WARPS);
         for (int b = 0; b < 2; ++b)
-            for (int m = 0; m < MAX_MT; ++m) { mbar_init(&bars->act_ready[b][m], EPI_THREADS); mbar_init(&bars->acc_full[b][m], 1); }
+            for (int m = 0; m < MAX_MT; ++m) { mbar_init(&bars->act_ready[b][m], 2 * EPI_WARPS); mbar_init(&bars->acc_full[b][m], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int l = 0; l < L; ++l)
             for (int h = 0; h < H; ++h) { tma_prefetch_desc(&maps.w[l][h][0]); tma_prefetch_desc(&maps.w[l][h][1]); }
     }
-    if (warp == MMA_WARP0) tmem_alloc(&bars->tmem_holder, 512);
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();    // the peers' barriers exist before anything is multicast to them
-    tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_holder;
+    // The gather warps do not wait for the set-up (barrier init, TMEM allocation, cluster handshake ~3000 cycles): they start on
+    // the batch's indices at once and only join before their first mbarrier arrive (BAR_INIT / cluster wait in the gather code).
+    const bool gather_warp = warp >= G_WARP0;
+    uint32_t tmem_base = 0;
+    if (gather_warp) {
+        if (CL > 1) cluster_arrive();
+    } else {
+        if (warp == MMA_WARP0) tmem_alloc(&bars->tmem_holder, 512);
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_CORE), "n"(32 * G_WARP0) : "memory");
+        if (CL > 1) { cluster_arrive(); cluster_wait(); }   // the peers' barriers exist before anything is multicast to them
+        tc_fence_after();
+        tmem_base = bars->tmem_holder;
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_INIT), "n"(NTHREADS) : "memory");      // releases the gather warps
+    }
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
     // every CTA of a cluster runs the same number of tiles (the weight rings are shared); tiles past the end are dummies
     const int n_iter = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
     auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
     auto layer_n = [&](int l) { return pad16(p.widths[l]); };
+
+    // ---------------------------------------------------------------- one tile's epilogue for 16 of the 32 samples
+    // Run by the four epilogue warps (half 0: samples 0..15) and by four gather warps once their tile's interaction is done
+    // (half 1: samples 16..31) -- warp % 4 selects the TMEM lane quarter, so two warps share each quarter on different columns.
+    auto epilogue_pass = [&](int it, int half, uint32_t tbase, uint32_t& acc_bits) {
+        const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row = q4 * 32 + lane;
+        const uint32_t taddr_row = tbase + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(16 * half);
+        const int s_base = 16 * half;
+        float zsum = 0.f;                              // lanes 2j, 2j+1: sum over this warp's neurons of relu(.) * fc for one sample
+        for (int l = 0; l < L; ++l) {
+            const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad);
+            const bool last = (l == L - 1);
+            for (int mt = 0; mt < MT; ++mt) {
+                // The output of tile mt overwrites chunks 2mt, 2mt+1 of the SAME activation buffer the layer reads, so every MMA
+                // reading them must have finished: both issuers interleave their tiles chunk by chunk, hence once the first tile
+                // of each ring (0 and 1) is complete all chunks but the last are dead; the last chunk is written by the last
+                // tile, by which time every acc_full of the layer has been waited for.
+                // this neuron's bias / net_1_fc weight: issued before the wait so their L2 latency hides behind it
+                const int n = mt * 128 + row;
+                const int rows_valid = min(128, npad - mt * 128);   // neurons [N, npad) are zero rows: they write the K padding
+                const bool real = row < rows_valid && n < N;
+                const float bb = real ? __ldg(p.bias[l] + n) : 0.f;
+                const float ff = (real && last) ? __ldg(p.fc + n) : 0.f;
+                const int nwait = (mt == 0 && MT > 1) ? 2 : (mt == 1 ? 0 : 1);
+                for (int w = 0; w < nwait; ++w) {
+                    const int t = mt + w, bit = buf * MAX_MT + t;
+                    FZ_PROG(8 + 4 * half + q4, (l << 16) | (t << 4) | (6 << 24));
+                    mbar_wait(&bars->acc_full[buf][t], (acc_bits >> bit) & 1u, p.err, 31);
+                    acc_bits ^= 1u << bit;
+                }
+                FZ_PROG(8 + 4 * half + q4, (l << 16) | (mt << 4) | (7 << 24));
+                if (threadIdx.x == 32 * EPI_WARP0 && it == 0 && l < 4 && mt == 0) FZ_CLK(8 + 2 * l);
+                tc_fence_after();
+                if (q4 * 32 < rows_valid) {                     // warp-uniform: some lane of this quarter holds a neuron
+                    uint32_t d[16];
+                    tmem_ld16(taddr_row + (uint32_t)(buf * 256 + mt * NB), d);
+                    float v[16];
+                    if constexpr (SPLIT) {
+                        uint32_t d2[16];
+                        tmem_ld16(taddr_row + (uint32_t)(buf * 256 + mt * NB + 32), d2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) v[s] = __uint_as_float(d[s]) + __uint_as_float(d2[s]);
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) v[s] = __uint_as_float(d[s]);
+                    }
+                    if (last) {
+                        // net_1_fc dot: this neuron's contribution to each sample, then a transpose-reduction over the warp's 32
+                        // neurons: 8 + 4 + 2 + 1 + 1 shuffles leave the sum for sample s16 in lanes 2 s16' and 2 s16' + 1
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) v[s] = fmaxf(v[s] + bb, 0.f) * ff;
+#pragma unroll
+                        for (int off = 16, nn = 16; off >= 2; off >>= 1, nn >>= 1) {
+                            const bool upper = (lane & off) != 0;
+#pragma unroll
+                            for (int i = 0; i < nn / 2; ++i) {
+                                const float send = upper ? v[i] : v[i + nn / 2];
+                                const float keep = upper ? v[i + nn / 2] : v[i];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        zsum += v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                    } else if (row < rows_valid) {
+                        // element (sample s, k = n) of the next operand: chunk n/64, row s (hi) / 32+s (lo), 16-byte unit
+                        // ((n%64)/8) ^ (row%8), byte (n%8)*2
+                        unsigned char* xc = sX + (size_t)(n >> 6) * CH + (n & 7) * 2 + s_base * 128;
+                        const int u = (n & 63) >> 3;
+#pragma unroll
+                        for (int s = 0; s < 16; ++s) {
+                            const float a = fmaxf(v[s] + bb, 0.f);
+                            const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+                            unsigned char* dst = xc + s * 128 + ((u ^ (s & 7)) << 4);     // (s_base + s) % 8 == s % 8
+                            *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                            if constexpr (SPLIT)
+                                *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(a - __bfloat162float(hi));
+                        }
+                    }
+                }
+                if (!last) {
+                    fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
+                    tc_fence_before();             // TMEM reads ordered before the arrive
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->act_ready[(l + 1) & 1][mt]);
+                }
+                if (threadIdx.x == 32 * EPI_WARP0 && it == 0 && l < 4 && mt == MT - 1) FZ_CLK(9 + 2 * l);
+            }
+        }
+        // lane -> sample of its sum: bits 4..1 of the lane index, most significant first
+        const int s16 = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        if ((lane & 1) == 0) bars->red[half * 4 + q4][s16] = zsum;
+        tc_fence_before();
+    };
 
     if (warp < RINGS) {
         // ================================================================= TMA producers: warp 0 feeds ring 0 (even neuron tiles),
@@ -247,7 +354,10 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                 const uint32_t idAlo = make_idesc(rowsA, 32), idBlo = make_idesc(rowsB, 32);
                 for (int c = 0; c < kch; ++c) {
                     if (l == 0) {
-                        if (c == 0) { if (it == 0 && lane == 0 && mw == 0) FZ_CLK(0); mbar_wait(&bars->x_ready, (uint32_t)(it & 1), p.err, 21); if (it == 0 && lane == 0 && mw == 0) FZ_CLK(1); }
+                        // layer 1 starts on chunk c as soon as the gather group has written it
+                        if (c == 0 && it == 0 && lane == 0 && mw == 0) FZ_CLK(0);
+                        mbar_wait(&bars->x_ready[c], (uint32_t)(it & 1), p.err, 21);
+                        if (c == 0 && it == 0 && lane == 0 && mw == 0) FZ_CLK(1);
                     } else if ((c & 1) == 0) {
                         // chunks c, c+1 hold neurons [64c, 64c+128) of the previous layer = its neuron tile c/2
                         const int g = c >> 1, bit = buf * MAX_MT + g;
@@ -325,109 +435,25 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
             }
         }
     } else if (warp < G_WARP0) {
-        // ================================================================= epilogue warps (thread = neuron)
-        const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
-        const int row = q4 * 32 + lane;
-        const int ewarp = warp - EPI_WARP0;
-        const uint32_t taddr_row = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        // ================================================================= epilogue warps (thread = neuron), samples 0..15
         uint32_t acc_bits = 0;                         // phase parity of acc_full[buf][mt], bit buf * MAX_MT + mt
         for (int it = 0; it < n_iter; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            float zsum = 0.f;                              // lane s: sum over this warp's neurons of relu(.) * fc for sample s
-            for (int l = 0; l < L; ++l) {
-                const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad);
-                const bool last = (l == L - 1);
-                for (int mt = 0; mt < MT; ++mt) {
-                    // The output of tile mt overwrites chunks 2mt, 2mt+1 of the SAME activation buffer the layer reads, so every
-                    // MMA reading them must have finished: both issuers interleave their tiles chunk by chunk, hence once the first
-                    // tile of each ring (0 and 1) is complete all chunks but the last are dead; the last chunk is written by the
-                    // last tile, by which time every acc_full of the layer has been waited for.
-                    const int nwait = (mt == 0 && MT > 1) ? 2 : (mt == 1 ? 0 : 1);
-                    for (int w = 0; w < nwait; ++w) {
-                        const int t = mt + w, bit = buf * MAX_MT + t;
-                        FZ_PROG(8 + ewarp, (l << 16) | (t << 4) | (6 << 24));
-                        mbar_wait(&bars->acc_full[buf][t], (acc_bits >> bit) & 1u, p.err, 31);
-                        acc_bits ^= 1u << bit;
-                    }
-                    FZ_PROG(8 + ewarp, (l << 16) | (mt << 4) | (7 << 24));
-                    if (threadIdx.x == 32 * EPI_WARP0 && it == 0 && l < 4 && mt == 0) FZ_CLK(8 + 2 * l);
-                    tc_fence_after();
-                    const int n = mt * 128 + row;
-                    const int rows_valid = min(128, npad - mt * 128);   // neurons [N, npad) are zero rows: they write the K padding
-                    if (q4 * 32 < rows_valid) {                     // warp-uniform: some lane of this quarter holds a neuron
-                        uint32_t d[32];
-                        tmem_ld32(taddr_row + (uint32_t)(buf * 256 + mt * NB), d);
-                        float v[32];
-                        if constexpr (SPLIT) {
-                            uint32_t d2[32];
-                            tmem_ld32(taddr_row + (uint32_t)(buf * 256 + mt * NB + 32), d2);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int s = 0; s < TS; ++s) v[s] = __uint_as_float(d[s]) + __uint_as_float(d2[s]);
-                        } else {
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int s = 0; s < TS; ++s) v[s] = __uint_as_float(d[s]);
-                        }
-                        if (last) {
-                            // net_1_fc dot: this neuron's contribution to each sample, then a transpose-reduction over the
-                            // warp's 32 neurons (31 shuffles): lane s ends with the sum for sample s
-                            const bool real = row < rows_valid && n < N;
-                            const float bb = real ? __ldg(p.bias[l] + n) : 0.f;
-                            const float ff = real ? __ldg(p.fc + n) : 0.f;
-#pragma unroll
-                            for (int s = 0; s < TS; ++s) v[s] = fmaxf(v[s] + bb, 0.f) * ff;
-#pragma unroll
-                            for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
-                                const bool upper = (lane & off) != 0;
-#pragma unroll
-                                for (int i = 0; i < nn / 2; ++i) {
-                                    const float send = upper ? v[i] : v[i + nn / 2];
-                                    const float keep = upper ? v[i + nn / 2] : v[i];
-                                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                                }
-                            }
-                            zsum += v[0];
-                        } else if (row < rows_valid) {
-                            const float bb = n < N ? __ldg(p.bias[l] + n) : 0.f;
-                            // element (sample s, k = n) of the next operand: chunk n/64, row s (hi) / 32+s (lo), 16-byte unit
-                            // ((n%64)/8) ^ (row%8), byte (n%8)*2
-                            unsigned char* xc = sX + (size_t)(n >> 6) * CH + (n & 7) * 2;
-                            const int u = (n & 63) >> 3;
-#pragma unroll
-                            for (int s = 0; s < TS; ++s) {
-                                const float a = fmaxf(v[s] + bb, 0.f);
-                                const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-                                unsigned char* dst = xc + s * 128 + ((u ^ (s & 7)) << 4);
-                                *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-                                if constexpr (SPLIT)
-                                    *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(a - __bfloat162float(hi));
-                            }
-                        }
-                    }
-                    if (!last) {
-                        fence_async_smem();            // generic-proxy stores -> visible to the tensor-core (async) proxy
-                        tc_fence_before();             // TMEM reads ordered before the arrive
-                        mbar_arrive(&bars->act_ready[(l + 1) & 1][mt]);
-                    }
-                    if (threadIdx.x == 32 * EPI_WARP0 && it == 0 && l < 4 && mt == MT - 1) FZ_CLK(9 + 2 * l);
-                }
-            }
-            bars->red[ewarp][lane] = zsum;
-            asm volatile("bar.sync %0, %1;" ::"n"(BAR_EPI), "n"(EPI_THREADS) : "memory");
-            if (ewarp == 0) {
+            epilogue_pass(it, 0, tmem_base, acc_bits);
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_EPI), "n"(2 * EPI_THREADS) : "memory");
+            if (warp == EPI_WARP0) {
                 mbar_wait(&bars->shallow_ready, (uint32_t)(it & 1), p.err, 33);
                 const long long b = (long long)tile * TS + lane;
                 float z = bars->shallow[lane];
 #pragma unroll
-                for (int w = 0; w < EPI_WARPS; ++w) z += bars->red[w][lane];
+                for (int q = 0; q < 4; ++q) z += bars->red[(lane >> 4) * 4 + q][lane & 15];
                 if (b < p.B) {
                     if (p.logits) p.logits[b] = z;
                     if (p.prob) p.prob[b] = 1.0f / (1.0f + expf(-z));
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&bars->tile_done);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tile_done);
             if (threadIdx.x == 32 * EPI_WARP0 && it == 0) FZ_CLK(16);
         }
     } else {
@@ -442,12 +468,21 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
         sm.idx = reinterpret_cast<int32_t*>(base + p.oIdx);
         sm.xv = reinterpret_cast<float*>(base + p.oXv);
         sm.EP = e_pitch(FK);
+        uint32_t helper_acc_bits = 0;
+        bool joined = false;
+        auto join_core = [&]() {          // first use of the mbarriers: the set-up by the other warps (and the peers') is complete
+            if (!joined) {
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_INIT), "n"(NTHREADS) : "memory");
+                if (CL > 1) cluster_wait();
+                joined = true;
+            }
+        };
         for (int it = 0; it < n_iter; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int64_t b0 = (int64_t)tile * TS;
             int64_t left = p.ep.B - b0;
             const int nrows = (int)(left < 0 ? 0 : (left > TS ? TS : left));
-            if (it > 0) mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 40);      // the previous tile is done with X
+            if (it > 0) { join_core(); mbar_wait(&bars->tile_done, (uint32_t)((it - 1) & 1), p.err, 40); }   // the previous tile is done with X
             float first_acc[G_ROUNDS];
             long long* gclk = (p.clk && it == 0) ? p.clk + blockIdx.x * FZ_NCLK + 96 : nullptr;
             embed_gather<FT, KT, TS, G_ROUNDS, BAR_GATHER>(p.ep, sm, base + p.oImg, it == 0, gtid, G_THREADS, b0, nrows, first_acc, gclk);
@@ -486,6 +521,13 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
 #pragma unroll
                 for (int f = 0; f < FTc; ++f) e[f] = owner ? myE[f * KTc] : 0.f;
                 group_sync<BAR_GATHER>(G_THREADS);          // every thread holds its values: the block may be overwritten
+                join_core();
+                for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
+                    const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
+                    unsigned char* dst = sX + (size_t)(col >> 6) * CH + s * 128 + ((((col & 63) >> 3) ^ (s & 7)) << 4) + (col & 7) * 2;
+                    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
+                    if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(0.f);
+                }
                 if (owner) {
 #pragma unroll
                     for (int f = 0; f < FTc; ++f) {
@@ -496,14 +538,12 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                         if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
                     }
                 }
-                for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
-                    const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
-                    unsigned char* dst = sX + (size_t)(col >> 6) * CH + s * 128 + ((((col & 63) >> 3) ^ (s & 7)) << 4) + (col & 7) * 2;
-                    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
-                    if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(0.f);
-                }
+                // One release for the whole operand: signalling chunk by chunk lets layer 1 start ~1700 cycles earlier, but its
+                // MMA + TMA traffic then saturates shared memory and the remaining column stores (and phase D) crawl -- measured
+                // slower end to end.
                 fence_async_smem();
-                mbar_arrive(&bars->x_ready);
+                __syncwarp();
+                if ((gtid & 31) == 0) for (int c = 0; c < (Kp + KCH - 1) / KCH; ++c) mbar_arrive(&bars->x_ready[c]);
                 if (gtid == 0 && it == 0) FZ_CLK(21);
                 if (gclk && gtid == 0) gclk[5] = clock64();
                 if (owner) {
@@ -545,7 +585,8 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                     for (int k = 0; k < KTc; ++k) tot += sm.part[k * TS + gtid];
                     bars->shallow[gtid] = tot + __ldg(p.ep.bias);
                 }
-                mbar_arrive(&bars->shallow_ready);
+                __syncwarp();
+                if ((gtid & 31) == 0) mbar_arrive(&bars->shallow_ready);
                 if (gtid == 0 && it == 0) FZ_CLK(22);
             } else {
                 // ---- generic shapes: separate fp32 block -> bf16 (hi | lo) operand of layer 1, then the pair-list interaction
@@ -579,12 +620,23 @@ fused_forward_kernel(const __grid_constant__ Maps maps, const __grid_constant__ 
                     *reinterpret_cast<uint4*>(dst) = hi4;
                     if constexpr (SPLIT) *reinterpret_cast<uint4*>(dst + 32 * 128) = lo4;
                 }
+                join_core();
                 fence_async_smem();
-                mbar_arrive(&bars->x_ready);
+                __syncwarp();
+                if ((gtid & 31) == 0) for (int c = 0; c < (Kp + KCH - 1) / KCH; ++c) mbar_arrive(&bars->x_ready[c]);
                 if (gtid == 0 && it == 0) FZ_CLK(21);
                 embed_interact<FT, KT, TS, G_ROUNDS, BAR_GATHER, true>(p.ep, sm, gtid, G_THREADS, nrows, first_acc, bars->shallow, gclk, nullptr);
-                mbar_arrive(&bars->shallow_ready);
+                __syncwarp();
+                if ((gtid & 31) == 0) mbar_arrive(&bars->shallow_ready);
                 if (gtid == 0 && it == 0) FZ_CLK(22);
+            }
+            // ---- the first four gather warps now serve as the second epilogue set (samples 16..31) of this tile
+            if (warp < G_WARP0 + EPI_WARPS) {
+                tc_fence_after();
+                epilogue_pass(it, 1, bars->tmem_holder, helper_acc_bits);
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_EPI), "n"(2 * EPI_THREADS) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->tile_done);
             }
         }
     }
