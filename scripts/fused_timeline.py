@@ -32,6 +32,9 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(3); run(0); run(1); run(2); e1.record(); torch.cuda.synchronize(); fn(None)
 print(f"4 back-to-back launches: {e0.elapsed_time(e1) * 250:.1f} us per launch (CUDA events)")
 c = clk.cpu().numpy().reshape(148, NCLK)[:nc].astype(np.float64)
+if (c[:, 0] == 0).any():          # pair kernel: only the leader CTA of a pair has MMA threads; use the leaders' rows
+    c = c[c[:, 0] != 0]
+    nc = len(c)
 t0 = c[:, 0:1]          # MMA thread reaches the x_ready wait
 rel = c - t0
 names = {20: "gather done (E block)", 21: "X written (bf16)", 1: "x_ready seen by MMA", 22: "shallow done", 16: "tile done"}
@@ -50,3 +53,8 @@ print("  " + " ".join(f"{np.median(rel[:, 96 + k]):9.0f}" for k in range(7)))
 print(f"kernel entry -> MMA thread start: median {np.median(-rel[:, 28]):.0f} cycles; MMA start -> exit: {np.median(rel[:, 30]):.0f} cycles")
 g0, g1 = c[:, 29], c[:, 31]
 print(f"globaltimer: first CTA entry -> last CTA exit {g1.max() - g0.min():.0f} ns; CTA entry spread {g0.max() - g0.min():.0f} ns; per-CTA lifetime median {np.median(g1 - g0):.0f} ns")
+
+if c[:, 40].any():
+    print("layer-1 epilogue of warp 4 (median): per pair-tile: start, TMEM loaded, stores issued, proxy fence done")
+    for j in range(2):
+        print("  tile", j, " ".join(f"{np.median(rel[:, 40 + 4 * j + k]):9.0f}" for k in range(4)))

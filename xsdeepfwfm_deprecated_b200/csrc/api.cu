@@ -247,6 +247,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
     // the internal streams start after everything already queued on the caller's stream (weights, images)
     DFW_CUDA_OK(cudaEventRecord(hp->start, main_st));
     for (int i = 0; i < kSlots; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
+    static const int dbg_skip = getenv("DFW_E2E_SKIP") ? atoi(getenv("DFW_E2E_SKIP")) : 0;   // debug: 1 = no H2D, 2 = no kernels
     int64_t done = 0;
     for (int64_t i = 0; done < N; ++i, done += batch) {
         const int64_t b = N - done < batch ? N - done : batch;
@@ -257,13 +258,14 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         float* xv = reinterpret_cast<float*>(ws + H.oXv);
         float* logit = reinterpret_cast<float*>(ws + H.oLogit);
         float* prob = reinterpret_cast<float*>(ws + H.oProb);
-        if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host + done * C, (size_t)b * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (C > 0 && dbg_skip != 1 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host + done * C, (size_t)b * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (num > 0 && dbg_skip != 1 && dbg_skip != 3 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (dbg_skip < 2)
         if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, b, precision, ws + H.oFwd, slot_bytes - H.oFwd,
                                  logits_host ? logit : nullptr, prob_host ? prob : nullptr, nullptr, st))
             return rc;
         if (logits_host) DFW_CUDA_OK(cudaMemcpyAsync(logits_host + done, logit, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (prob_host) DFW_CUDA_OK(cudaMemcpyAsync(prob_host + done, prob, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (prob_host && dbg_skip != 3) DFW_CUDA_OK(cudaMemcpyAsync(prob_host + done, prob, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kSlots; ++i) {
         DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));

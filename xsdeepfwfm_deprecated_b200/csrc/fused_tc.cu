@@ -37,83 +37,13 @@
 //   input overwrites layer l's; the fp32 gather block aliases it) | ring 0 | ring 1 | shallow image | misc
 //   TMEM: 2 x 256 columns (layer parity) x (<= 4 neuron tiles x 32|64 sample columns)
 //   Limits of the fused form: depth <= 4, widths <= 512, F*K <= 512, K <= 20.  Other shapes take the staged path.
-#include <stdlib.h>
-#include <string.h>
-
-#include "embed_device.cuh"
-#include "tc_common.cuh"
+#include "fused_common.cuh"
+#include "fused_pair.cuh"
 
 namespace dfw {
 namespace fz {
 
 using namespace dfw::tc;
-
-constexpr int TS = 32;                         // samples per tile
-constexpr int G_WARPS = 10;
-constexpr int G_THREADS = 32 * G_WARPS;
-constexpr int EPI_WARPS = 4;
-constexpr int EPI_THREADS = 32 * EPI_WARPS;
-constexpr int RINGS = 2;                       // weight rings; one producer warp and one MMA warp per ring
-constexpr int MMA_WARP0 = RINGS;               // producers: warps 0..1, MMA issuers: warps 2..3
-constexpr int EPI_WARP0 = 2 * RINGS;           // epilogue warps 4..7: warp % 4 == TMEM lane quarter
-constexpr int G_WARP0 = EPI_WARP0 + EPI_WARPS; // gather warps 8..17
-constexpr int NTHREADS = 32 * G_WARP0 + G_THREADS;         // 576 (18 warps: 96 registers per thread)
-constexpr int STAGE_BYTES = 128 * 128;         // one weight box: 128 neurons x 64 bf16
-constexpr int RING_MAX = 6;                    // stages per ring
-constexpr int MAX_L = 4;
-constexpr int MAX_MT = 4;                      // 128-neuron tiles per layer (width <= 512)
-constexpr int MAX_W = 512;
-constexpr int G_ROUNDS = 2;                    // phase-D rounds of the gather group (generic shapes): K <= G_ROUNDS * G_WARPS
-constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_INIT = 3, BAR_CORE = 4;     // named barriers
-constexpr int MAX_KCH = 8;                     // 64-wide K chunks of the widest operand (512)
-constexpr size_t SMEM_LIMIT = 227 * 1024;
-
-struct alignas(64) Maps {
-    CUtensorMap w[MAX_L][2][2];                // [layer][hi | lo][128-row tile | 64-row last tile]
-};
-
-struct Params {
-    EmbedParams ep;
-    int depth, in_dim;
-    int widths[MAX_L];
-    const float* bias[MAX_L];
-    const float* fc;
-    float* logits;
-    float* prob;
-    long long B;
-    int num_tiles, cluster;
-    int x_chunks;                               // 64-wide K chunks of the activation buffer
-    int nst[2];                                 // stages of ring 0 / ring 1
-    uint32_t oE, oRing, oImg, oPart, oIdx, oXv, oMisc;   // shared-memory offsets from the 1024-aligned base (X is at 0)
-    int* err;
-    long long* clk;                             // optional per-CTA timeline (debug tooling): FZ_NCLK x int64 per CTA
-    volatile int* prog;                         // optional progress markers in pinned host memory (debug): 32 ints per CTA
-};
-#define FZ_PROG(slot, val) do { if (p.prog && lane == 0) p.prog[blockIdx.x * 32 + (slot)] = (val); } while (0)
-#define FZ_NCLK 128
-#define FZ_CLK(slot) do { if (p.clk) p.clk[blockIdx.x * FZ_NCLK + (slot)] = clock64(); } while (0)
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-
-// neuron tiles of a layer of (padded) width npad: 128 rows each; a last tile of <= 16 rows runs as M = 64
-__host__ __device__ inline int n_mtiles(int npad) { return (npad + 127) / 128; }
-__host__ __device__ inline int mtile_rows(int npad, int mt) {
-    const int rem = npad - mt * 128;
-    return rem >= 128 ? 128 : (rem <= 16 ? 64 : 128);
-}
-
-// The symmetrised field matrix as a kernel parameter (same column layout as the shallow image's U).  valid = 0: absent.
-constexpr int MAX_U = 1152;                    // usize(47) + 4 = 1108 floats
-struct alignas(16) UParam { int valid; int pad_[3]; float u[MAX_U]; };
 
 struct Bars {
     uint64_t full[2][RING_MAX], empty[2][RING_MAX];
@@ -122,11 +52,6 @@ struct Bars {
     uint32_t tmem_holder, pad_;
     float shallow[TS];
     float red[2 * EPI_WARPS][16];                 // [sample half * 4 + lane quarter][sample % 16]
-};
-
-struct RingPos {
-    uint32_t s, ph;
-    __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1; } }
 };
 
 // ---------------------------------------------------------------------------------------- the kernel
@@ -703,7 +628,8 @@ static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why
     p.oE = 0;
     if (!alias) { p.oE = (uint32_t)o; o += (ts.bE + 1023) / 1024 * 1024; }
     p.oRing = (uint32_t)o;
-    const size_t tail = up16(img_layout(F, K).total) + ts.bPart + ts.bIdx + ts.bXv + up16(sizeof(Bars)) + 64;
+    const size_t bars_bytes = sizeof(Bars) > sizeof(PairBars) ? sizeof(Bars) : sizeof(PairBars);
+    const size_t tail = up16(img_layout(F, K).total) + ts.bPart + ts.bIdx + ts.bXv + up16(bars_bytes) + 64;
     // two rings; a SPLIT iteration takes 2 stages of a ring (hi + lo box), so its rings hold an even number of stages
     const int min_ring = 2;
     if (o + tail + 1024 + 2 * (size_t)min_ring * STAGE_BYTES > SMEM_LIMIT) { *why = "shared memory: the two weight rings do not fit"; return false; }
@@ -717,7 +643,7 @@ static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why
     o += ts.bPart;                        p.oIdx = (uint32_t)o;
     o += ts.bIdx;                         p.oXv = (uint32_t)o;
     o += ts.bXv;                          p.oMisc = (uint32_t)((o + 15) & ~size_t(15));
-    o = p.oMisc + sizeof(Bars);
+    o = p.oMisc + bars_bytes;
     pl.smem_bytes = o + 1024;
     return true;
 }
@@ -823,9 +749,35 @@ static int env_cluster() {
     return v;
 }
 
+static int env_pair() {
+    static const int v = env_int("DFW_FUSED_PAIR", 1);
+    return v;
+}
+
+// cta_group::2 pair kernel (fused_pair.cuh): CTA b owns tile b, CTAs (2q, 2q+1) form a pair
+template <bool SPLIT, int FT, int KT>
+static int launch_pair(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st) {
+    Params& p = pl.p;
+    p.cluster = 2;
+    if (int rc = get_maps(m, SPLIT, 1, p.in_dim, maps)) return rc;       // whole 128-row boxes: each CTA loads its own tile
+    auto kern = fused_pair_kernel<SPLIT, FT, KT>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((p.num_tiles + 1) / 2 * 2);
+    kern<<<grid, NTHREADS, pl.smem_bytes, st>>>(maps, pl.up, pl.p);
+    count_launch();
+    return check_launch("fused_pair_kernel");
+}
+
 template <bool SPLIT, int FT, int KT>
 static int run(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st) {
     Params& p = pl.p;
+    if constexpr (FT > 0) {
+        if (env_pair() && p.num_tiles >= 2) return launch_pair<SPLIT, FT, KT>(m, pl, maps, st);
+    }
     // cluster size: the largest of {4, 2, 1} that still covers all tiles in the fewest waves
     int best_cl = 1, best_grid = 1, best_iter = 1 << 30;
     for (int cl = 4; cl >= 1; cl >>= 1) {
