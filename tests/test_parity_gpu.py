@@ -384,3 +384,21 @@ def test_streamed_host_inference_matches_forward():
         assert np.array_equal(got_p, prob.cpu().numpy()), precision
         got_p2 = m.predict_proba_host(Xi, Xv, batch_size=8192)
         assert np.array_equal(got_p2, got_p), precision
+
+
+@pytest.mark.parametrize("nodes,depth", [(300, 3), (136, 2), (64, 1), (16, 3), (250, 4), (512, 2), (520, 2)])
+def test_fused_kernels_odd_widths_and_depths(nodes, depth):
+    """Neuron-tile edge cases of the fused kernels: an odd number of 128-neuron tiles (the pair kernel's second CTA then has no
+    tile in the last pair), widths that are not multiples of 16 or 64, one-tile layers (ring 1 idle), depth 1..4, and a width
+    above the fused limit (520 > 512: staged fallback).  Criteo shape, so the CTA-pair kernel runs for B > 32."""
+    cfg = PathConfig(39, [1] * 13 + [50 + 37 * i for i in range(26)], use_fm=False, use_fwfm=True, use_deep=True,
+                     use_fwlw=True, deep_nodes=nodes, h_depth=depth)
+    w = synth.make_weights(cfg, seed=nodes + depth)
+    for B in (20, 333):
+        Xi, Xv = synth.make_inputs(cfg, B, seed=B + nodes)
+        ref = closed_form.forward(cfg, w, Xi, Xv)
+        for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", BF16_REL, 2e-2 * np.abs(ref["deep"]).max())):
+            if nodes > 512 and precision == "bf16":
+                continue            # bf16 has no staged form for widths > 512 (documented limit); bf16x3 falls back to fp32
+            got = run(to_cuda(cfg, w, precision=precision), Xi, Xv)
+            assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], rel) + extra, (precision, B)

@@ -40,7 +40,7 @@ struct PairBars {
     uint64_t fin;                    // per CTA: the 8 partial-sum blocks of its samples are in `red`
     uint32_t tmem_holder, pad_;
     float shallow[TS];
-    float red[2][EPI_WARPS][TS];     // [source CTA][lane quarter][sample]
+    float red[2][2][EPI_WARPS][TS];  // [source CTA][pair-tile][lane quarter][sample]
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
-        if (spin > (1u << 24)) {
+        if (spin > (1u << 28)) {     // ~10 s: only a broken pipeline gets here (profilers and debuggers stretch waits a lot)
             if (err) atomicExch(err, code);
             __trap();
         }
@@ -91,8 +91,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// 20 warps: 0-1 producers, 2-3 MMA issuers, 4-7 epilogue set A, 8-17 gather group (8-11 = set B, 12-15 = set C once their tile's
+// interaction is done), 16-19 = set D (18-19 do nothing else).  Set (j, h) = (pair-tile, sample half): A (0,0) B (0,1) C (1,0) D (1,1),
+// so the four (tile, half) units of a layer's epilogue run side by side.
+constexpr int PAIR_WARPS = G_WARP0 + G_WARPS + 2;
+constexpr int PAIR_THREADS = 32 * PAIR_WARPS;      // 640 (5 warps per scheduler: 96 registers per thread)
+constexpr int PAIR_CORE_THREADS = 32 * (G_WARP0 + 2);
+
 template <bool SPLIT, int FT, int KT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UParam up, const Params p) {
     static_assert(FT > 0 && KT > 0 && KT <= G_WARPS, "the pair kernel is built for the specialised shapes only");
     constexpr int NB = SPLIT ? 64 : 32;                 // rows of one K chunk of the activation buffer: hi [| lo] of 32 samples
@@ -119,7 +126,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             for (int s = 0; s < RING_MAX; ++s) { mbar_init(&bars->full[r][s], 1); mbar_init(&bars->empty[r][s], 1); }
         mbar_init(&bars->x_ready, 2 * G_WARPS);
         mbar_init(&bars->shallow_ready, G_WARPS);
-        mbar_init(&bars->fin, 2 * EPI_WARPS);
+        mbar_init(&bars->fin, 4 * EPI_WARPS);        // sets (0,h) and (1,h) of both CTAs
         for (int b = 0; b < 2; ++b) {
             for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], 2 * EPI_WARPS);
             for (int j = 0; j < 2; ++j) mbar_init(&bars->acc_full[b][j], 1);
@@ -128,7 +135,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         for (int l = 0; l < L; ++l)
             for (int h = 0; h < H; ++h) tma_prefetch_desc(&maps.w[l][h][0]);
     }
-    const bool gather_warp = warp >= G_WARP0;
+    const bool gather_warp = warp >= G_WARP0 && warp < G_WARP0 + G_WARPS;
     uint32_t tmem_base = 0;
     if (gather_warp) {
         cluster_arrive();
@@ -138,11 +145,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
         tc_fence_before();
-        asm volatile("bar.sync %0, %1;" ::"n"(BAR_CORE), "n"(32 * G_WARP0) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_CORE), "n"(PAIR_CORE_THREADS) : "memory");
         cluster_arrive(); cluster_wait();        // both CTAs' barriers and TMEM exist before anything crosses over
         tc_fence_after();
         tmem_base = bars->tmem_holder;
-        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_INIT), "n"(NTHREADS) : "memory");
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_INIT), "n"(PAIR_THREADS) : "memory");
     }
     const int tile = (int)blockIdx.x;                   // one wave: CTA b owns tile b
 
@@ -151,7 +158,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
 
     // ---------------------------------------------------------------- epilogue of this CTA's neuron tiles for one sample half
     // half h = sample columns [32h, 32h + 32) = the samples of CTA h: activations and partial sums are stored into CTA h
-    auto epilogue_pass = [&](int half, uint32_t tbase) {
+    auto epilogue_pass = [&](int jset, int half, uint32_t tbase) {
         const int q4 = warp & 3;
         const int row = q4 * 32 + lane;
         const uint32_t taddr_row = tbase + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(32 * half);
@@ -161,14 +168,15 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         for (int l = 0; l < L; ++l) {
             const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
             const bool last = (l == L - 1);
-            for (int j = 0; j < PT; ++j) {
+            {
+                const int j = jset;                                 // this set's pair-tile (it may not exist in a narrow layer)
                 const int t = 2 * j + (int)rank;                    // this CTA's neuron tile of pair-tile j
                 const int n = t * 128 + row;
                 const int rows_valid = max(0, min(128, npad - t * 128));
                 const bool real = row < rows_valid && n < N;
                 const float bb = real ? __ldg(p.bias[l] + n) : 0.f;
                 const float ff = (real && last) ? __ldg(p.fc + n) : 0.f;
-                if (j == 0) {
+                {
                     // the tile outputs overwrite the activation buffers the layer still reads: wait for every pair-tile of the layer
                     for (int w = 0; w < PT; ++w) {
                         const int bit = buf * 2 + w;
@@ -178,7 +186,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     }
                 }
                 FZ_PROG(8 + 4 * half + q4, (l << 16) | (j << 4) | (7 << 24));
-                if (threadIdx.x == 32 * EPI_WARP0 && l < 4 && j == 0) FZ_CLK(8 + 2 * l);
+                if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(8 + 2 * l);
                 tc_fence_after();
                 const bool stamp = p.clk && threadIdx.x == 32 * EPI_WARP0 && l == 0;
                 if (stamp) FZ_CLK(40 + 4 * j);
@@ -224,11 +232,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->act_ready[(l + 1) & 1][t]), 0));
                 }
-                if (threadIdx.x == 32 * EPI_WARP0 && l < 4 && j == PT - 1) FZ_CLK(9 + 2 * l);
+                if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(9 + 2 * l);
             }
         }
         // lane s holds this warp's partial sum for sample s of CTA `half`
-        st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][q4][lane]), (uint32_t)half), zsum);
+        st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][jset][q4][lane]), (uint32_t)half), zsum);
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -341,7 +349,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         }
     } else if (warp < G_WARP0) {
         // ================================================================= epilogue warps: sample columns 0..31 (CTA 0's samples)
-        epilogue_pass(0, tmem_base);
+        epilogue_pass(0, 0, tmem_base);
         if (warp == EPI_WARP0) {
             // this CTA's samples: shallow part + the partial sums of both CTAs' neuron tiles
             mbar_wait_cluster(&bars->fin, 0, p.err, 34);
@@ -351,13 +359,18 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) z += bars->red[r][q][lane];
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) z += bars->red[r][j][q][lane];
             if (b < p.B) {
                 if (p.logits) p.logits[b] = z;
                 if (p.prob) p.prob[b] = 1.0f / (1.0f + expf(-z));
             }
             if (lane == 0) FZ_CLK(16);
         }
+    } else if (!gather_warp) {
+        // ================================================================= warps 18-19: the second half of epilogue set D
+        epilogue_pass(1, 1, tmem_base);
     } else {
         // ================================================================= gather group (register path of fused_tc.cu)
         const int gtid = threadIdx.x - 32 * G_WARP0;
@@ -405,7 +418,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
 #pragma unroll
         for (int f = 0; f < FT; ++f) e[f] = owner ? myE[f * KT] : 0.f;
         group_sync<BAR_GATHER>(G_THREADS);          // every thread holds its values: the block may be overwritten
-        asm volatile("bar.sync %0, %1;" ::"n"(BAR_INIT), "n"(NTHREADS) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_INIT), "n"(PAIR_THREADS) : "memory");
         cluster_wait();                             // set-up of both CTAs complete: barriers may be used
         for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
             const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
@@ -469,10 +482,11 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         __syncwarp();
         if ((gtid & 31) == 0) mbar_arrive(&bars->shallow_ready);
         if (gtid == 0) FZ_CLK(22);
-        // ---- the first four gather warps are the epilogue set of sample columns 32..63 (CTA 1's samples)
-        if (warp < G_WARP0 + EPI_WARPS) {
+        // ---- the gather warps now serve in the epilogue sets B (8-11), C (12-15) and D (16-17, with warps 18-19)
+        {
+            const int set = (warp - EPI_WARP0) >> 2;        // 1, 2, 3
             tc_fence_after();
-            epilogue_pass(1, bars->tmem_holder);
+            epilogue_pass(set >> 1, set & 1, bars->tmem_holder);
         }
     }
 

@@ -651,7 +651,10 @@ static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why
 template <bool SPLIT, int FT, int KT>
 static int launch(const Maps& maps, const Plan& pl, int grid, cudaStream_t st) {
     auto kern = fused_forward_kernel<SPLIT, FT, KT>;
-    static thread_local bool configured = false;
+    static thread_local bool configured_dev[16] = {};       // per device: function attributes are per context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 15];
     if (!configured) {
         DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -761,13 +764,16 @@ static int launch_pair(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st
     p.cluster = 2;
     if (int rc = get_maps(m, SPLIT, 1, p.in_dim, maps)) return rc;       // whole 128-row boxes: each CTA loads its own tile
     auto kern = fused_pair_kernel<SPLIT, FT, KT>;
-    static thread_local bool configured = false;
+    static thread_local bool configured_dev[16] = {};       // per device: function attributes are per context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 15];
     if (!configured) {
         DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         configured = true;
     }
     const unsigned grid = (unsigned)((p.num_tiles + 1) / 2 * 2);
-    kern<<<grid, NTHREADS, pl.smem_bytes, st>>>(maps, pl.up, pl.p);
+    kern<<<grid, PAIR_THREADS, pl.smem_bytes, st>>>(maps, pl.up, pl.p);
     count_launch();
     return check_launch("fused_pair_kernel");
 }

@@ -388,7 +388,10 @@ extern "C" int dfw_mlp_bf16(const dfw_model* m, const void* Xb, int64_t ldXb, in
     const size_t smem_bytes = tc::SMEM_FIXED + (size_t)p.a_chunks * tc::A_CHUNK_BYTES + (size_t)p.nstage * p.stage_bytes;
     p.err = (workspace && workspace_bytes >= 4) ? static_cast<int*>(workspace) : nullptr;
     p.clk = tc::g_clk;
-    static thread_local bool configured = false;
+    static thread_local bool configured_dev[16] = {};       // per device: function attributes are per context
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 15];
     if (!configured) {
         DFW_CUDA_OK(cudaFuncSetAttribute(tc::mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_LIMIT));
         configured = true;

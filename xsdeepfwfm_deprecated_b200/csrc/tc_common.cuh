@@ -35,7 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
-        if (spin > (1u << 24)) {
+        if (spin > (1u << 28)) {     // ~10 s: only a broken pipeline gets here (profilers and debuggers stretch waits a lot)
             if (err) atomicExch(err, code);
             __trap();
         }
