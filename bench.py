@@ -102,10 +102,11 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- workload
-def make_model(device, precision, feature_sizes, world=1, exchange="p2p"):
+def make_model(device, precision, feature_sizes, world=1, exchange="p2p", index_dtype="int64"):
     from xsdeepfwfm_deprecated_b200.model import DeepFMs
     kw = dict(embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False, use_fwfm=True, use_deep=True,
-              use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision)
+              use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision,
+              index_dtype=index_dtype)
     if world > 1:
         from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
         m = ShardedDeepFMs(FIELD, feature_sizes, exchange=exchange, shard_threshold=200, **kw)
@@ -354,6 +355,38 @@ def run_ours(args):
                ms_per_step=round(t_e2e / args.steps * 1e3, 4),
                api=f"dfw_forward_host_stream (pinned host Xi/Xv -> H2D -> forward + sigmoid -> D2H into pinned host memory, "
                    f"every step; 3 rotating streams, one host sync per {nh} steps); timed with the host clock")
+    # supplementary: the same end-to-end path fed with the packed int32 index format (DFW_XI_INT32); the
+    # headline e2e above keeps the reference's int64 indices
+    if world == 1:
+        try:
+            m32 = make_model(device, args.precision, sizes, 1, index_dtype="int32")
+            p32 = m32._get_plan()
+            p32.ensure_image(m32, args.precision)
+            hXi32 = hXi.to(torch.int32).pin_memory()
+
+            def e2e32(k):
+                done = 0
+                while done < k:
+                    n = min(nh, k - done)
+                    rc = lib.dfw_forward_host_stream(p32.model_ref, hXi32.data_ptr(), hXv.data_ptr(), n * B, B, prec,
+                                                     hws.data_ptr(), hws.numel(), None, hout.data_ptr(), sp)
+                    if rc:
+                        _lib.check(rc, "dfw_forward_host_stream")
+                    done += n
+
+            ref_out = hout[0].clone()
+            e2e32(max(3, args.warmup))
+            assert torch.equal(hout[0], ref_out), "int32-index path differs from int64"
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            e2e32(args.steps)
+            torch.cuda.synchronize(device)
+            t32 = time.perf_counter() - t0
+            e2e["int32_indices"] = dict(value=round(B * args.steps / t32, 1), unit=UNIT,
+                                        h2d_bytes_per_step=B * (26 * 4 + NUM * 4), ms_per_step=round(t32 / args.steps * 1e3, 4))
+            del m32
+        except Exception as ex:        # supplementary only: never lose the bench line over it
+            e2e["int32_indices"] = {"error": str(ex)[:200]}
     clk = clocks.stop() if rank == 0 else None
 
     cpu = None

@@ -54,6 +54,10 @@ extern "C" {
 #define DFW_USE_LW     (1u << 2) /* first order projected by fm_1st                 model/DeepFMs.py:445-450 */
 #define DFW_USE_DEEP   (1u << 3) /* MLP term                                        model/DeepFMs.py:395-436 */
 #define DFW_CHECK_INDEX (1u << 8) /* out-of-range Xi sets *err_word (and reads row 0) instead of UB */
+#define DFW_XI_INT32   (1u << 9) /* every Xi buffer of this model (device and host) holds int32 elements, not int64 -- the packed input
+                                    format of SURVEY 8(f): all Criteo / Twitter cardinalities fit, and indices are 80 % of the bytes a
+                                    host batch sends over PCIe.  Strides stay in elements; the `const int64_t*` parameters are then
+                                    plain addresses of int32 data */
 
 /* qr_op of a table (model/QREmbeddingBag.py:167-172) */
 #define DFW_TABLE_PLAIN 0

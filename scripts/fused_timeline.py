@@ -49,6 +49,9 @@ for k in order:
 
 print("gather group phases (median): start, image+idx regs, idx in smem, rows issued, E complete, interact start, phase D done")
 print("  " + " ".join(f"{np.median(rel[:, 96 + k]):9.0f}" for k in range(7)))
+if c[:, 96 + 8].any():
+    print("operand write (median): values in registers, group sync, joined set-up, columns stored, proxy fence done")
+    print("  " + " ".join(f"{np.median(rel[:, 96 + k]):9.0f}" for k in range(8, 13)))
 
 print(f"kernel entry -> MMA thread start: median {np.median(-rel[:, 28]):.0f} cycles; MMA start -> exit: {np.median(rel[:, 30]):.0f} cycles")
 g0, g1 = c[:, 29], c[:, 31]

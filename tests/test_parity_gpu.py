@@ -402,3 +402,23 @@ def test_fused_kernels_odd_widths_and_depths(nodes, depth):
                 continue            # bf16 has no staged form for widths > 512 (documented limit); bf16x3 falls back to fp32
             got = run(to_cuda(cfg, w, precision=precision), Xi, Xv)
             assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], rel) + extra, (precision, B)
+
+
+def test_int32_index_format_is_bit_identical():
+    """DFW_XI_INT32: the packed int32 input format gives the same bits as the reference's int64, through
+    forward (fused and staged kernels) and through the streamed host path; a wrong index dtype is refused."""
+    c = load_case("qr_mult_fwlw")
+    cfg = c["cfg"]
+    Xi, Xv = synth.make_inputs(cfg, 700, seed=5)
+    for precision in ("bf16x3", "fp32"):
+        m64 = to_cuda(cfg, c["weights"], precision=precision)
+        m32 = to_cuda(cfg, c["weights"], precision=precision, index_dtype="int32")
+        a = run(m64, Xi, Xv)
+        with torch.no_grad():
+            b = m32(torch.from_numpy(Xi.astype(np.int32)).cuda(), torch.from_numpy(Xv).cuda()).cpu().numpy()
+        assert np.array_equal(a, b), precision
+        pa = m64.predict_proba_host(Xi, Xv, batch_size=256)
+        pb = m32.predict_proba_host(Xi.astype(np.int32), Xv, batch_size=256)
+        assert np.array_equal(pa, pb), precision
+        with pytest.raises(TypeError):
+            m32(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda())

@@ -148,7 +148,7 @@ HostLayout host_layout(const dfw_model* m, int64_t B, int precision) {
     HostLayout H;
     const int C = m->field_size - m->numerical;
     size_t o = 0;
-    H.oXi = o;    o += align_up((size_t)B * (C > 0 ? C : 1) * sizeof(int64_t), 256);
+    H.oXi = o;    o += align_up((size_t)B * (C > 0 ? C : 1) * sizeof(int64_t), 256);      // sized for int64; int32 uses half
     H.oXv = o;    o += align_up((size_t)B * (m->numerical > 0 ? m->numerical : 1) * sizeof(float), 256);
     H.oLogit = o; o += align_up((size_t)B * sizeof(float), 256);
     H.oProb = o;  o += align_up((size_t)B * sizeof(float), 256);
@@ -179,7 +179,8 @@ extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, cons
     float* xv = reinterpret_cast<float*>(ws + H.oXv);
     float* logit = reinterpret_cast<float*>(ws + H.oLogit);
     float* prob = reinterpret_cast<float*>(ws + H.oProb);
-    if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host, (size_t)B * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    const size_t ib = (m->flags & DFW_XI_INT32) ? sizeof(int32_t) : sizeof(int64_t);
+    if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host, (size_t)B * C * ib, cudaMemcpyHostToDevice, st));
     if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host, (size_t)B * num * sizeof(float), cudaMemcpyHostToDevice, st));
     if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, B, precision, ws + H.oFwd, workspace_bytes - H.oFwd,
                              logits_host ? logit : nullptr, prob_host ? prob : nullptr, nullptr, stream))
@@ -247,6 +248,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
     // the internal streams start after everything already queued on the caller's stream (weights, images)
     DFW_CUDA_OK(cudaEventRecord(hp->start, main_st));
     for (int i = 0; i < kSlots; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
+    const size_t ib = (m->flags & DFW_XI_INT32) ? sizeof(int32_t) : sizeof(int64_t);
     static const int dbg_skip = getenv("DFW_E2E_SKIP") ? atoi(getenv("DFW_E2E_SKIP")) : 0;   // debug: 1 = no H2D, 2 = no kernels
     int64_t done = 0;
     for (int64_t i = 0; done < N; ++i, done += batch) {
@@ -258,7 +260,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         float* xv = reinterpret_cast<float*>(ws + H.oXv);
         float* logit = reinterpret_cast<float*>(ws + H.oLogit);
         float* prob = reinterpret_cast<float*>(ws + H.oProb);
-        if (C > 0 && dbg_skip != 1 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xi, xi_host + done * C, (size_t)b * C * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (C > 0 && dbg_skip != 1 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xi, reinterpret_cast<const char*>(xi_host) + (size_t)done * C * ib, (size_t)b * C * ib, cudaMemcpyHostToDevice, st));
         if (num > 0 && dbg_skip != 1 && dbg_skip != 3 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
         if (dbg_skip < 2)
         if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, b, precision, ws + H.oFwd, slot_bytes - H.oFwd,

@@ -198,6 +198,12 @@ template <int S> __device__ __forceinline__ int owner_col(int tid, int nthreads,
     else return tid / S + r * (nthreads / S);
 }
 
+// one index of the batch: int64 as the reference feeds it, or int32 (DFW_XI_INT32)
+__device__ __forceinline__ int64_t load_index(const EmbedParams& p, int64_t elem) {
+    if (p.flags & DFW_XI_INT32) return (int64_t)__ldg(reinterpret_cast<const int32_t*>(p.xi) + elem);
+    return __ldg(p.xi + elem);
+}
+
 // ------------------------------------------------------------------------------------------ phases A + B
 // Fills sm.E (S x EP, rows >= nrows zeroed), sm.idx, sm.xv for samples [b0, b0 + nrows).  Returns through
 // first_acc[r] the first-order table partial (use_fwlw = 0) of this thread's (sample, column) of round r.
@@ -233,7 +239,7 @@ __device__ __forceinline__ void embed_gather(const EmbedParams& p, const TileSme
 #pragma unroll
         for (int r = 0; r < kMaxIdx; ++r) {
             myidx[r] = 0; mycol[r] = (int)st.r;
-            if (tid + r * nthreads < nIdx && (int)st.q < nrows) myidx[r] = p.xi[(b0 + st.q) * p.xi_sb + st.r * p.xi_sc];
+            if (tid + r * nthreads < nIdx && (int)st.q < nrows) myidx[r] = load_index(p, (b0 + st.q) * p.xi_sb + st.r * p.xi_sc);
             st.next();
         }
         DivStep sv(tid, nthreads, num > 0 ? num : 1);
@@ -278,7 +284,7 @@ __device__ __forceinline__ void embed_gather(const EmbedParams& p, const TileSme
 #pragma unroll 1
     for (uint32_t e = tid + kMaxIdx * nthreads; e < (uint32_t)nIdx; e += nthreads) {    // small groups only
         const uint32_t s = e / (uint32_t)C, c = e - s * C;
-        int64_t idx = (int)s < nrows ? p.xi[(b0 + s) * p.xi_sb + c * p.xi_sc] : 0;
+        int64_t idx = (int)s < nrows ? load_index(p, (b0 + s) * p.xi_sb + c * p.xi_sc) : 0;
         if (idx < 0 || idx >= sF[num + c].rows) {
             if (p.err) atomicExch(p.err, 1 + num + c);
             idx = 0;

@@ -417,9 +417,12 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         float e[FT];
 #pragma unroll
         for (int f = 0; f < FT; ++f) e[f] = owner ? myE[f * KT] : 0.f;
+        if (gclk && gtid == 0) gclk[8] = clock64();
         group_sync<BAR_GATHER>(G_THREADS);          // every thread holds its values: the block may be overwritten
+        if (gclk && gtid == 0) gclk[9] = clock64();
         asm volatile("bar.sync %0, %1;" ::"n"(BAR_INIT), "n"(PAIR_THREADS) : "memory");
         cluster_wait();                             // set-up of both CTAs complete: barriers may be used
+        if (gclk && gtid == 0) gclk[10] = clock64();
         for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
             const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
             unsigned char* dst = sX + (size_t)(col >> 6) * CH + s * 128 + ((((col & 63) >> 3) ^ (s & 7)) << 4) + (col & 7) * 2;
@@ -436,7 +439,9 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
             }
         }
+        if (gclk && gtid == 0) gclk[11] = clock64();
         fence_async_smem();                         // these stores are local
+        if (gclk && gtid == 0) gclk[12] = clock64();
         __syncwarp();
         if ((gtid & 31) == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
         if (gtid == 0) FZ_CLK(21);

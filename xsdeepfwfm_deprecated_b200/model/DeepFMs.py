@@ -125,6 +125,8 @@ class _Plan:
             m.fm_1st = chk(owner.fm_1st.weight, "fm_1st.weight").data_ptr()
         if owner.check_index:
             flags |= _lib.CHECK_INDEX
+        if getattr(owner, "index_dtype", "int64") == "int32":
+            flags |= _lib.XI_INT32
         m.field_size, m.numerical, m.embedding_size = F, num, K
         m.fields = self.fields_dev.data_ptr()
         m.bias = chk(owner.bias, "bias").data_ptr()
@@ -223,7 +225,7 @@ class DeepFMs(nn.Module):
                  use_logit=0, embedding_bag=False, quantization_aware=False, dynamic_quantization=False,
                  static_quantization=False, static_calibrate=False,
                  qr_flag=0, qr_operation="mult", qr_collisions=1, qr_threshold=200, md_flag=0, md_threshold=200,
-                 logger=None, precision="fp32", check_index=False):
+                 logger=None, precision="fp32", check_index=False, index_dtype="int64"):
         super().__init__()
         self.field_size = field_size
         self.feature_sizes = feature_sizes
@@ -274,6 +276,11 @@ class DeepFMs(nn.Module):
         # extensions (keyword-only in spirit): MLP arithmetic and debug bounds checking
         self.precision = precision
         self.check_index = check_index
+        # "int64" is what the reference feeds (torch.LongTensor); "int32" is the packed input format: half the
+        # index bytes over PCIe.  Every Xi given to forward / predict_proba_host must then be int32.
+        if index_dtype not in ("int64", "int32"):
+            raise ValueError("index_dtype must be 'int64' or 'int32'")
+        self.index_dtype = index_dtype
         self._plan: Optional[_Plan] = None
         self._frozen = False
 
@@ -457,8 +464,9 @@ class DeepFMs(nn.Module):
         C_ = self.field_size - self.num
         if Xi.device != dev or Xv.device != dev:
             raise RuntimeError(f"inputs must be on {dev} (Xi on {Xi.device}, Xv on {Xv.device})")
-        if Xi.dtype != torch.int64:
-            raise TypeError("Xi must be int64 (torch.LongTensor), as the reference feeds it")
+        want = torch.int32 if self.index_dtype == "int32" else torch.int64
+        if Xi.dtype != want:
+            raise TypeError(f"Xi must be {want} (index_dtype={self.index_dtype!r}; the reference feeds torch.LongTensor)")
         if Xv.dtype != torch.float32:
             raise TypeError("Xv must be float32")
         B = Xi.shape[0]
@@ -521,14 +529,16 @@ class DeepFMs(nn.Module):
         plan.ensure_image(self, self.precision)
         n = len(Xi_np)
         C_ = self.field_size - self.num
-        Xi_np = np.ascontiguousarray(np.asarray(Xi_np, dtype=np.int64).reshape(n, C_))
+        np_idx = np.int32 if self.index_dtype == "int32" else np.int64
+        t_idx = torch.int32 if self.index_dtype == "int32" else torch.int64
+        Xi_np = np.ascontiguousarray(np.asarray(Xi_np, dtype=np_idx).reshape(n, C_))
         Xv_np = np.ascontiguousarray(np.asarray(Xv_np, dtype=np.float32).reshape(n, -1)[:, :self.num])
         bs = min(batch_size, max(n, 1))
         chunk = bs * max(1, min(batches_in_flight, -(-max(n, 1) // bs)))
         if plan.host_ws is None or plan.host_ws[0] != bs or plan.host_ws[1] != prec or plan.host_ws[2] < chunk:
             nbytes = lib.dfw_forward_host_stream_workspace_bytes(plan.model_ref, bs, prec)
             plan.host_ws = (bs, prec, chunk, torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev),
-                            torch.empty(chunk * C_, dtype=torch.int64).pin_memory(),
+                            torch.empty(chunk * C_, dtype=t_idx).pin_memory(),
                             torch.empty(chunk * max(self.num, 1), dtype=torch.float32).pin_memory(),
                             torch.empty(chunk, dtype=torch.float32).pin_memory(),
                             torch.empty(chunk, dtype=torch.float32).pin_memory())

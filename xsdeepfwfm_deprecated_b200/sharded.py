@@ -174,6 +174,8 @@ class ShardedDeepFMs(DeepFMs):
 
     def _forward_nccl(self, Xi, Xv, return_prob):
         """Baseline: index all-to-all -> owner gather -> row all-to-all -> fused kernel on per-batch tables."""
+        if self.index_dtype != "int64":
+            raise ValueError("the NCCL exchange baseline routes int64 indices; use exchange='p2p' with index_dtype='int32'")
         lib = _lib.load()
         group = self.process_group
         world = dist.get_world_size(group)
