@@ -87,3 +87,11 @@ def test_threshold_bisection_matches_oracle():
     t = m.binary_search_threshold(torch.from_numpy(w), 0.9, w.size)
     assert t == prune.bisect_threshold(w, 0.9, w.size)
     assert abs(float((np.abs(w) < t).mean()) - 0.9) < 1e-4
+
+
+def test_index_dtype_switch_is_validated():
+    c = load_case("deepfwfm_fwlw")
+    assert build(c["cfg"]).index_dtype == "int64"              # the reference's LongTensor format is the default
+    assert build(c["cfg"], index_dtype="int32").index_dtype == "int32"
+    with pytest.raises(ValueError):
+        build(c["cfg"], index_dtype="int16")

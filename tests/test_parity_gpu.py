@@ -422,3 +422,25 @@ def test_int32_index_format_is_bit_identical():
         assert np.array_equal(pa, pb), precision
         with pytest.raises(TypeError):
             m32(torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda())
+
+
+def test_concurrent_forwards_on_several_streams():
+    """bench.py spreads independent forwards over 3 streams (and a server would): the same module object must give the same
+    bits when its forwards overlap on the device."""
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    m = to_cuda(cfg, w, precision="bf16x3")
+    batches = [synth.make_inputs(cfg, 4096, seed=100 + i) for i in range(6)]
+    dev = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in batches]
+    with torch.no_grad():
+        want = [m(a, b).clone() for a, b in dev]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        got = [None] * len(dev)
+        for rep in range(5):
+            for i, (a, b) in enumerate(dev):
+                with torch.cuda.stream(streams[i % 3]):
+                    got[i] = m(a, b)
+        torch.cuda.synchronize()
+    for g, wnt in zip(got, want):
+        assert torch.equal(g, wnt)
