@@ -226,6 +226,14 @@ size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, int64_t batch
 int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t N, int64_t batch,
                             int precision, void* workspace, size_t workspace_bytes, float* logits_host, float* prob_host,
                             void* stream);
+/* Transport dfw_forward_host_stream will use for these buffers.  1 = "mapped": every buffer is pinned host memory the device
+ * can address (cudaHostAlloc / cudaHostRegister under unified addressing) and the fused kernel takes the model, so each
+ * batch is ONE launch whose gather warps load Xi / Xv over PCIe and whose epilogue stores logits / probabilities to host
+ * memory -- no copy-engine calls, no staging.  0 = "staged": cudaMemcpyAsync H2D -> kernels -> D2H per batch (pageable
+ * buffers, models outside the fused kernel's shapes).  Results are bit-identical.  DFW_HOST_TRANSPORT=copy|mapped in the
+ * environment forces one (mapped then fails with DFW_E_UNSUPPORTED where it cannot run). */
+int dfw_host_transport_is_mapped(const dfw_model* m, int precision, const void* xi_host, const void* xv_host,
+                                 const void* logits_host, const void* prob_host);
 
 /* ---- multi-GPU: row-sharded tables ------------------------------------------- */
 /* cudaMalloc'ed shard storage that can be exported to peers of the same node. */

@@ -444,3 +444,45 @@ def test_concurrent_forwards_on_several_streams():
         torch.cuda.synchronize()
     for g, wnt in zip(got, want):
         assert torch.equal(g, wnt)
+
+
+def test_host_transports_mapped_and_staged_are_bit_identical():
+    """dfw_forward_host_stream picks its transport from the buffers: pinned host memory -> the fused kernel loads Xi / Xv and
+    stores its results over PCIe itself ("mapped", one launch per batch); pageable memory -> staged cudaMemcpyAsync.  Same
+    bits either way, int64 and int32 indices, ragged last batch, logits and probabilities."""
+    import ctypes
+    from xsdeepfwfm_deprecated_b200 import _lib
+    lib = _lib.load()
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    N, bs = 4096 * 3 + 77, 4096
+    Xi, Xv = synth.make_inputs(cfg, N, seed=31)
+    for idt in ("int64", "int32"):
+        m = to_cuda(cfg, w, precision="bf16x3", index_dtype=idt)
+        plan = m._get_plan()
+        plan.ensure_image(m, "bf16x3")
+        prec = _lib.PRECISIONS["bf16x3"]
+        ws = torch.zeros(lib.dfw_forward_host_stream_workspace_bytes(plan.model_ref, bs, prec) + 4096, dtype=torch.uint8,
+                         device="cuda")
+        xi_page = torch.from_numpy(np.ascontiguousarray(Xi[:, :, 0].astype(idt)))
+        xv_page = torch.from_numpy(Xv.copy())
+        outs = {}
+        for name, pin in (("staged", False), ("mapped", True)):
+            xi_h = xi_page.pin_memory() if pin else xi_page
+            xv_h = xv_page.pin_memory() if pin else xv_page
+            lo = torch.full((N,), -7.0)
+            pr = torch.full((N,), -7.0)
+            if pin:
+                lo, pr = lo.pin_memory(), pr.pin_memory()
+            args = (xi_h.data_ptr(), xv_h.data_ptr(), lo.data_ptr(), pr.data_ptr())
+            assert lib.dfw_host_transport_is_mapped(plan.model_ref, prec, *args) == int(pin)
+            _lib.check(lib.dfw_forward_host_stream(plan.model_ref, args[0], args[1], N, bs, prec, ws.data_ptr(), ws.numel(),
+                                                   args[2], args[3], torch.cuda.current_stream().cuda_stream), name)
+            outs[name] = (lo.clone(), pr.clone())
+        assert torch.equal(outs["staged"][0], outs["mapped"][0]) and torch.equal(outs["staged"][1], outs["mapped"][1]), idt
+        with torch.no_grad():
+            idx = torch.from_numpy(Xi.astype(idt)).cuda()
+            want = m(idx, torch.from_numpy(Xv).cuda()).cpu()
+        assert torch.equal(outs["mapped"][0], want), idt
+        # the fp32 (staged-kernel) precision cannot use the mapped transport and says so
+        assert lib.dfw_host_transport_is_mapped(plan.model_ref, _lib.PRECISIONS["fp32"], *args) == 0

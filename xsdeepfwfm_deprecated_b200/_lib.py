@@ -77,6 +77,7 @@ SYMBOLS = {
     "dfw_forward_host": (C.c_int, [_MP, _vp, _vp, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp]),
     "dfw_forward_host_stream_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_forward_host_stream": (C.c_int, [_MP, _vp, _vp, _i64, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp]),
+    "dfw_host_transport_is_mapped": (C.c_int, [_MP, C.c_int, _vp, _vp, _vp, _vp]),
     "dfw_shard_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "dfw_shard_free": (C.c_int, [_vp]),
     "dfw_ipc_export": (C.c_int, [_vp, C.c_char_p]),

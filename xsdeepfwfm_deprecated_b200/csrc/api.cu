@@ -197,10 +197,11 @@ extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, cons
 // eval_by_batch / predict_proba do around forward (model/DeepFMs.py:750-784, 864-873) without their per-batch
 // .cuda() / .cpu() round trips.
 namespace {
-constexpr int kSlots = 3;
+constexpr int kSlots = 3;      // staged transport: slots of the device workspace = streams in rotation
+constexpr int kLanes = 6;      // mapped transport: streams in rotation (no staging, so more of them cost nothing)
 struct HostPipe {
-    cudaStream_t streams[kSlots] = {};
-    cudaEvent_t done[kSlots] = {};
+    cudaStream_t streams[kLanes] = {};
+    cudaEvent_t done[kLanes] = {};
     cudaEvent_t start = nullptr;
     int device = -1;
 };
@@ -212,7 +213,7 @@ int get_pipe(HostPipe** out) {
     DFW_REQUIRE(dev >= 0 && dev < 8, DFW_E_UNSUPPORTED, "device ordinal %d >= 8", dev);
     HostPipe& hp = g_pipe[dev];
     if (hp.device != dev) {
-        for (int i = 0; i < kSlots; ++i) {
+        for (int i = 0; i < kLanes; ++i) {
             DFW_CUDA_OK(cudaStreamCreateWithFlags(&hp.streams[i], cudaStreamNonBlocking));
             DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
         }
@@ -222,7 +223,42 @@ int get_pipe(HostPipe** out) {
     *out = &hp;
     return 0;
 }
+
+// Device-visible alias of a host buffer: pinned (cudaHostAlloc / cudaHostRegister) memory under unified addressing can be
+// loaded and stored by kernels directly over PCIe.  nullptr for pageable memory (which only a staged copy can move).
+void* mapped_alias(const void* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// 0 = choose (mapped when every buffer is device-visible and the fused kernel takes the model), 1 = staged copies, 2 = mapped
+int host_transport_override() {
+    static const int v = [] {
+        const char* e = getenv("DFW_HOST_TRANSPORT");
+        if (!e) return 0;
+        return !strcmp(e, "copy") ? 1 : !strcmp(e, "mapped") ? 2 : 0;
+    }();
+    return v;
+}
 }  // namespace
+
+extern "C" int dfw_host_transport_is_mapped(const dfw_model* m, int precision, const void* xi_host, const void* xv_host,
+                                            const void* logits_host, const void* prob_host) {
+    if (!m || check_model(m)) return 0;
+    if (host_transport_override() == 1 || getenv("DFW_NO_FUSED")) return 0;
+    const int C = m->field_size - m->numerical, num = m->numerical;
+    if (!(m->flags & DFW_USE_DEEP) || !(precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3) ||
+        !dfw_fused_supported(m, precision))
+        return 0;
+    if ((C > 0 && !mapped_alias(xi_host)) || (num > 0 && !mapped_alias(xv_host))) return 0;
+    if ((logits_host && !mapped_alias(logits_host)) || (prob_host && !mapped_alias(prob_host))) return 0;
+    return 1;
+}
 
 extern "C" size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, int64_t batch, int precision) {
     if (!m || batch <= 0) return 256;
@@ -247,8 +283,34 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
     const int C = m->field_size - m->numerical, num = m->numerical;
     // the internal streams start after everything already queued on the caller's stream (weights, images)
     DFW_CUDA_OK(cudaEventRecord(hp->start, main_st));
-    for (int i = 0; i < kSlots; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
+    for (int i = 0; i < kLanes; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
     const size_t ib = (m->flags & DFW_XI_INT32) ? sizeof(int32_t) : sizeof(int64_t);
+    if (dfw_host_transport_is_mapped(m, precision, xi_host, xv_host, logits_host, prob_host)) {
+        // Mapped transport: the host buffers are pinned, so the fused kernel loads each batch's indices / dense values and
+        // stores its results over PCIe itself -- the same bytes cross the bus, but there is one launch per batch, no copy-engine
+        // round trips and no staging; successive batches overlap on kLanes streams.
+        const char* xi_d = static_cast<const char*>(mapped_alias(xi_host));
+        const float* xv_d = static_cast<const float*>(mapped_alias(xv_host));
+        float* logit_d = static_cast<float*>(mapped_alias(logits_host));
+        float* prob_d = static_cast<float*>(mapped_alias(prob_host));
+        int64_t done = 0;
+        for (int64_t i = 0; done < N; ++i, done += batch) {
+            const int64_t b = N - done < batch ? N - done : batch;
+            if (int rc = dfw_forward_fused(m, reinterpret_cast<const int64_t*>(xi_d + (size_t)done * C * ib), C, 1,
+                                           xv_d ? xv_d + done * num : nullptr, num, 1, b, precision,
+                                           logit_d ? logit_d + done : nullptr, prob_d ? prob_d + done : nullptr, nullptr,
+                                           hp->streams[i % kLanes]))
+                return rc;
+        }
+        for (int i = 0; i < kLanes; ++i) {
+            DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));
+            DFW_CUDA_OK(cudaStreamWaitEvent(main_st, hp->done[i], 0));
+        }
+        DFW_CUDA_OK(cudaStreamSynchronize(main_st));
+        return 0;
+    }
+    DFW_REQUIRE(host_transport_override() != 2, DFW_E_UNSUPPORTED,
+                "DFW_HOST_TRANSPORT=mapped, but a host buffer is not pinned or the fused kernel does not take this model");
     static const int dbg_skip = getenv("DFW_E2E_SKIP") ? atoi(getenv("DFW_E2E_SKIP")) : 0;   // debug: 1 = no H2D, 2 = no kernels
     int64_t done = 0;
     for (int64_t i = 0; done < N; ++i, done += batch) {
