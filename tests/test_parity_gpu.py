@@ -333,7 +333,8 @@ def test_bf16x3_ragged_and_multi_tile(B):
     for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", BF16_REL, 2e-2 * np.abs(ref["deep"]).max())):
         got = run(to_cuda(cfg, c["weights"], precision=precision), Xi, Xv)
         assert got.shape == (B,)
-        assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], rel) + extra, precision
+        err = np.abs(got - ref["logit"]).max()
+        assert err <= logit_tol(ref["logit"], rel) + extra, (precision, B, float(err), int(np.abs(got - ref["logit"]).argmax()))
 
 
 def test_config2_full_size_batch_4096_bf16x3():

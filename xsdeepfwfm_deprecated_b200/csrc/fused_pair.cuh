@@ -54,6 +54,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 __device__ __forceinline__ void st_cluster_b16(uint32_t cluster_addr, __nv_bfloat16 v) {
     asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(cluster_addr), "h"(*reinterpret_cast<const uint16_t*>(&v)) : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+    return (uint32_t)*reinterpret_cast<const uint16_t*>(&lo) | ((uint32_t)*reinterpret_cast<const uint16_t*>(&hi) << 16);
+}
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
@@ -91,6 +97,23 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// The activation operand (B of every MMA) is stored SAMPLE-contiguous ("MN-major", no swizzle; layout and descriptor fields
+// checked by scripts/ubench/pair_mma_mn.cu): element (k, sample s) of a 64-wide K chunk lives at
+//     (s / 8) * X_SBO + k * 16 + (s % 8) * 2          core matrix = 8 k-rows x 8 samples = 128 contiguous bytes
+// so the epilogue thread of neuron k writes its 32 samples as four 16-byte stores (a warp: 512 contiguous bytes) instead of 32
+// scattered 2-byte stores into a K-major row.  X_SBO = 1024 + 32 keeps the gather group's 2-byte stores (a warp = 16 samples x
+// 2 adjacent k) conflict-free.  Descriptor: LBO = 128 (next 8 k), SBO = X_SBO (next 8 samples), K = 16 step = 256 bytes.
+constexpr uint32_t X_SBO = 1056;
+constexpr uint32_t X_HB = 4 * X_SBO;           // hi (or lo) part of one chunk: 32 samples x 64 k
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(X_SBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 // 20 warps: 0-1 producers, 2-3 MMA issuers, 4-7 epilogue set A, 8-17 gather group (8-11 = set B, 12-15 = set C once their tile's
 // interaction is done), 16-19 = set D (18-19 do nothing else).  Set (j, h) = (pair-tile, sample half): A (0,0) B (0,1) C (1,0) D (1,1),
 // so the four (tile, half) units of a layer's epilogue run side by side.
@@ -102,9 +125,8 @@ template <bool SPLIT, int FT, int KT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UParam up, const Params p) {
     static_assert(FT > 0 && KT > 0 && KT <= G_WARPS, "the pair kernel is built for the specialised shapes only");
-    constexpr int NB = SPLIT ? 64 : 32;                 // rows of one K chunk of the activation buffer: hi [| lo] of 32 samples
-    constexpr int CH = NB * 128;
     constexpr int H = SPLIT ? 2 : 1;
+    constexpr int CH = H * (int)X_HB;                   // one K chunk of the activation buffer: hi [| lo] of 32 samples
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sX = base;
@@ -128,7 +150,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         mbar_init(&bars->shallow_ready, G_WARPS);
         mbar_init(&bars->fin, 4 * EPI_WARPS);        // sets (0,h) and (1,h) of both CTAs
         for (int b = 0; b < 2; ++b) {
-            for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], 2 * EPI_WARPS);
+            for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], 4 * EPI_WARPS);
             for (int j = 0; j < 2; ++j) mbar_init(&bars->acc_full[b][j], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -156,51 +178,55 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
     auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
     auto layer_n = [&](int l) { return pad16(p.widths[l]); };
 
-    // ---------------------------------------------------------------- epilogue of this CTA's neuron tiles for one sample half
-    // half h = sample columns [32h, 32h + 32) = the samples of CTA h: activations and partial sums are stored into CTA h
-    auto epilogue_pass = [&](int jset, int half, uint32_t tbase) {
+    // ---------------------------------------------------------------- epilogue: set q = sample columns [16 q, 16 q + 16)
+    // The four sets (4 warps each, warp % 4 = TMEM lane quarter) split the 64 sample columns of a pair-tile four ways and walk
+    // this CTA's neuron tiles IN ORDER: tile j = 0 of every set first, then j = 1.  The operand chunks of the first tiles are
+    // therefore complete -- and the next layer's MMAs start -- when half of the layer's epilogue work is done; the second half
+    // runs under those MMAs.  Columns 16 q .. belong to the samples of CTA h = q / 2: activations and partial sums go to CTA h.
+    auto epilogue_pass = [&](int q, uint32_t tbase) {
         const int q4 = warp & 3;
         const int row = q4 * 32 + lane;
-        const uint32_t taddr_row = tbase + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(32 * half);
-        const uint32_t xdst = mapa_u32(smem_u32(sX), (uint32_t)half);           // activation buffer of the CTA owning these samples
+        const int half = q >> 1, sub = q & 1;
+        const uint32_t taddr_row = tbase + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(16 * q);
+        const uint32_t xdst = mapa_u32(smem_u32(sX), (uint32_t)half) + (uint32_t)(2 * sub) * X_SBO;   // n-groups 2 sub, 2 sub + 1
         uint32_t acc_bits = 0;
-        float zsum = 0.f;                              // lane s: sum over this warp's neurons of relu(.) * fc for sample s of CTA `half`
+        float zsum[2] = {0.f, 0.f};                    // per pair-tile: this warp's neurons' relu(.) * fc, sample 16 sub + lane / 2 of CTA `half`
         for (int l = 0; l < L; ++l) {
             const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
             const bool last = (l == L - 1);
-            {
-                const int j = jset;                                 // this set's pair-tile (it may not exist in a narrow layer)
+            // the tile outputs overwrite the activation buffer the layer still reads: wait for every pair-tile of the layer
+            for (int w = 0; w < PT; ++w) {
+                const int bit = buf * 2 + w;
+                FZ_PROG(8 + 4 * q + q4, (l << 16) | (w << 4) | (6 << 24));
+                mbar_wait(&bars->acc_full[buf][w], (acc_bits >> bit) & 1u, p.err, 31);
+                acc_bits ^= 1u << bit;
+            }
+            if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(8 + 2 * l);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (j >= PT) break;
                 const int t = 2 * j + (int)rank;                    // this CTA's neuron tile of pair-tile j
                 const int n = t * 128 + row;
                 const int rows_valid = max(0, min(128, npad - t * 128));
                 const bool real = row < rows_valid && n < N;
                 const float bb = real ? __ldg(p.bias[l] + n) : 0.f;
                 const float ff = (real && last) ? __ldg(p.fc + n) : 0.f;
-                {
-                    // the tile outputs overwrite the activation buffers the layer still reads: wait for every pair-tile of the layer
-                    for (int w = 0; w < PT; ++w) {
-                        const int bit = buf * 2 + w;
-                        FZ_PROG(8 + 4 * half + q4, (l << 16) | (w << 4) | (6 << 24));
-                        mbar_wait(&bars->acc_full[buf][w], (acc_bits >> bit) & 1u, p.err, 31);
-                        acc_bits ^= 1u << bit;
-                    }
-                }
-                FZ_PROG(8 + 4 * half + q4, (l << 16) | (j << 4) | (7 << 24));
-                if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(8 + 2 * l);
-                tc_fence_after();
+                FZ_PROG(8 + 4 * q + q4, (l << 16) | (j << 4) | (7 << 24));
                 const bool stamp = p.clk && threadIdx.x == 32 * EPI_WARP0 && l == 0;
                 if (stamp) FZ_CLK(40 + 4 * j);
                 if (q4 * 32 < rows_valid) {
-                    uint32_t d[32];
-                    tmem_ld32(taddr_row + (uint32_t)(buf * 128 + j * 64), d);
+                    uint32_t d[16];
+                    tmem_ld16(taddr_row + (uint32_t)(buf * 128 + j * 64), d);
                     tmem_ld_wait();
                     if (stamp) FZ_CLK(41 + 4 * j);
                     if (last) {
-                        float v[32];
+                        float v[16];
 #pragma unroll
-                        for (int s = 0; s < 32; ++s) v[s] = fmaxf(__uint_as_float(d[s]) + bb, 0.f) * ff;
+                        for (int s = 0; s < 16; ++s) v[s] = fmaxf(__uint_as_float(d[s]) + bb, 0.f) * ff;
+                        // transpose-reduce over the warp's 32 neurons: after the four steps lane pair (2 s, 2 s + 1) holds sample s
 #pragma unroll
-                        for (int off = 16, nn = 32; off >= 1; off >>= 1, nn >>= 1) {
+                        for (int off = 16, nn = 16; off >= 2; off >>= 1, nn >>= 1) {
                             const bool upper = (lane & off) != 0;
 #pragma unroll
                             for (int i = 0; i < nn / 2; ++i) {
@@ -209,18 +235,27 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                                 v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                             }
                         }
-                        zsum += v[0];
+                        zsum[j] += v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
                     } else if (row < rows_valid) {
-                        // element (sample s, k = n) of the next operand in CTA `half`: chunk n/64, row s (hi) / 32+s (lo)
-                        const uint32_t xc = xdst + (uint32_t)((n >> 6) * CH + (n & 7) * 2);
-                        const int u = (n & 63) >> 3;
+                        // 16 samples of k = n in the next operand of CTA `half`: chunk n / 64, two groups of 8 samples
+                        const uint32_t xc = xdst + (uint32_t)((n >> 6) * CH + (n & 63) * 16);
 #pragma unroll
-                        for (int s = 0; s < 32; ++s) {
-                            const float a = fmaxf(__uint_as_float(d[s]) + bb, 0.f);
-                            const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-                            const uint32_t dst = xc + (uint32_t)(s * 128 + ((u ^ (s & 7)) << 4));
-                            st_cluster_b16(dst, hi);
-                            if constexpr (SPLIT) st_cluster_b16(dst + 32 * 128, __float2bfloat16_rn(a - __bfloat162float(hi)));
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t wh[4], wl[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float a0 = fmaxf(__uint_as_float(d[8 * g + 2 * i]) + bb, 0.f);
+                                const float a1 = fmaxf(__uint_as_float(d[8 * g + 2 * i + 1]) + bb, 0.f);
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);        // .x = a0 (low half)
+                                wh[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                if constexpr (SPLIT) {
+                                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(wh[i] << 16),
+                                                                                      a1 - __uint_as_float(wh[i] & 0xffff0000u));
+                                    wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                                }
+                            }
+                            st_cluster_v4(xc + g * X_SBO, wh[0], wh[1], wh[2], wh[3]);
+                            if constexpr (SPLIT) st_cluster_v4(xc + g * X_SBO + X_HB, wl[0], wl[1], wl[2], wl[3]);
                         }
                     }
                 }
@@ -232,11 +267,15 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->act_ready[(l + 1) & 1][t]), 0));
                 }
-                if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(9 + 2 * l);
             }
+            if (threadIdx.x == 32 * EPI_WARP0 && l < 4) FZ_CLK(9 + 2 * l);
         }
-        // lane s holds this warp's partial sum for sample s of CTA `half`
-        st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][jset][q4][lane]), (uint32_t)half), zsum);
+        // lane pair (2 s, 2 s + 1) holds this warp's partial sums for sample 16 sub + s of CTA `half`
+        if ((lane & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][j][q4][16 * sub + (lane >> 1)]), (uint32_t)half), zsum[j]);
+        }
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
         tc_fence_before();
         __syncwarp();
@@ -284,7 +323,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             uint64_t* empty = bars->empty[mw];
             const uint32_t sW_u32 = smem_u32(sW) + (mw ? NS0 * (uint32_t)STAGE_BYTES : 0u);
             const uint32_t sX_u32 = smem_u32(sX);
-            const uint32_t idesc = make_idesc(256, 64);
+            const uint32_t idesc = make_idesc(256, 64) | (1u << 16);     // B is MN-major
             RingPos rp{0, 0};
             uint32_t act_bits = 0;
             for (int l = 0; l < L; ++l) {
@@ -307,8 +346,8 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     }
                     if (!active) continue;
                     const int ks = min(4, (K - c * KCH) / 16);
-                    const uint64_t bhi = make_desc_sw128(sX_u32 + (uint32_t)(c * CH));
-                    const uint64_t blo = make_desc_sw128(sX_u32 + (uint32_t)(c * CH + 32 * 128));
+                    const uint64_t bhi = make_desc_mn(sX_u32 + (uint32_t)(c * CH));
+                    const uint64_t blo = make_desc_mn(sX_u32 + (uint32_t)(c * CH) + X_HB);
                     const uint32_t acc0 = c ? 1u : 0u;
                     const bool last_c = c == kch - 1;
                     RingPos s0 = rp, s1 = rp;
@@ -322,21 +361,21 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     const uint64_t al = make_desc_sw128(sW_u32 + s1.s * (uint32_t)STAGE_BYTES);
                     if (elect_one()) {
                         umma_bf16_2cta(dcol, ah, bhi, idesc, acc0);
-                        if (ks > 1) umma_bf16_2cta(dcol, ah + 2, bhi + 2, idesc, 1u);
-                        if (ks > 2) umma_bf16_2cta(dcol, ah + 4, bhi + 4, idesc, 1u);
-                        if (ks > 3) umma_bf16_2cta(dcol, ah + 6, bhi + 6, idesc, 1u);
+                        if (ks > 1) umma_bf16_2cta(dcol, ah + 2, bhi + 16, idesc, 1u);
+                        if (ks > 2) umma_bf16_2cta(dcol, ah + 4, bhi + 32, idesc, 1u);
+                        if (ks > 3) umma_bf16_2cta(dcol, ah + 6, bhi + 48, idesc, 1u);
                         if (SPLIT) {
                             umma_bf16_2cta(dcol, ah, blo, idesc, 1u);                 // W_hi X_lo
-                            if (ks > 1) umma_bf16_2cta(dcol, ah + 2, blo + 2, idesc, 1u);
-                            if (ks > 2) umma_bf16_2cta(dcol, ah + 4, blo + 4, idesc, 1u);
-                            if (ks > 3) umma_bf16_2cta(dcol, ah + 6, blo + 6, idesc, 1u);
+                            if (ks > 1) umma_bf16_2cta(dcol, ah + 2, blo + 16, idesc, 1u);
+                            if (ks > 2) umma_bf16_2cta(dcol, ah + 4, blo + 32, idesc, 1u);
+                            if (ks > 3) umma_bf16_2cta(dcol, ah + 6, blo + 48, idesc, 1u);
                         }
                         umma_commit_2cta(&empty[s0.s]);
                         if (SPLIT) {
                             umma_bf16_2cta(dcol, al, bhi, idesc, 1u);                 // W_lo X_hi
-                            if (ks > 1) umma_bf16_2cta(dcol, al + 2, bhi + 2, idesc, 1u);
-                            if (ks > 2) umma_bf16_2cta(dcol, al + 4, bhi + 4, idesc, 1u);
-                            if (ks > 3) umma_bf16_2cta(dcol, al + 6, bhi + 6, idesc, 1u);
+                            if (ks > 1) umma_bf16_2cta(dcol, al + 2, bhi + 16, idesc, 1u);
+                            if (ks > 2) umma_bf16_2cta(dcol, al + 4, bhi + 32, idesc, 1u);
+                            if (ks > 3) umma_bf16_2cta(dcol, al + 6, bhi + 48, idesc, 1u);
                             umma_commit_2cta(&empty[s1.s]);
                         }
                         if (last_c) umma_commit_2cta(&bars->acc_full[buf][mw]);
@@ -349,7 +388,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         }
     } else if (warp < G_WARP0) {
         // ================================================================= epilogue warps: sample columns 0..31 (CTA 0's samples)
-        epilogue_pass(0, 0, tmem_base);
+        epilogue_pass(0, tmem_base);
         if (warp == EPI_WARP0) {
             // this CTA's samples: shallow part + the partial sums of both CTAs' neuron tiles
             mbar_wait_cluster(&bars->fin, 0, p.err, 34);
@@ -370,7 +409,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         }
     } else if (!gather_warp) {
         // ================================================================= warps 18-19: the second half of epilogue set D
-        epilogue_pass(1, 1, tmem_base);
+        epilogue_pass(3, tmem_base);
     } else {
         // ================================================================= gather group (register path of fused_tc.cu)
         const int gtid = threadIdx.x - 32 * G_WARP0;
@@ -425,18 +464,18 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         if (gclk && gtid == 0) gclk[10] = clock64();
         for (int i = gtid; i < TS * (Kp - FK); i += G_THREADS) {     // K padding columns [F*K, Kp) are zero
             const int s = i / (Kp - FK), col = FK + (i - s * (Kp - FK));
-            unsigned char* dst = sX + (size_t)(col >> 6) * CH + s * 128 + ((((col & 63) >> 3) ^ (s & 7)) << 4) + (col & 7) * 2;
+            unsigned char* dst = sX + (size_t)(col >> 6) * CH + (s >> 3) * X_SBO + (col & 63) * 16 + (s & 7) * 2;
             *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
-            if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(0.f);
+            if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HB) = __float2bfloat16_rn(0.f);
         }
         if (owner) {
 #pragma unroll
             for (int f = 0; f < FT; ++f) {
                 const int col = f * KT + kk;
-                unsigned char* dst = sX + (size_t)(col >> 6) * CH + smp * 128 + ((((col & 63) >> 3) ^ (smp & 7)) << 4) + (col & 7) * 2;
+                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (smp >> 3) * X_SBO + (col & 63) * 16 + (smp & 7) * 2;
                 const __nv_bfloat16 hi = __float2bfloat16_rn(e[f]);
                 *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + 32 * 128) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
+                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HB) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
             }
         }
         if (gclk && gtid == 0) gclk[11] = clock64();
@@ -491,7 +530,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         {
             const int set = (warp - EPI_WARP0) >> 2;        // 1, 2, 3
             tc_fence_after();
-            epilogue_pass(set >> 1, set & 1, bars->tmem_holder);
+            epilogue_pass(set, bars->tmem_holder);
         }
     }
 

@@ -618,7 +618,9 @@ static bool make_plan(const dfw_model* m, bool split, Plan& pl, const char** why
     }
     Params& p = pl.p;
     const bool alias = specialised(F, K);          // the register path: the fp32 gather block lives inside the activation buffer
-    const int NB = split ? 64 : 32, CH = NB * 128;
+    // one 64-wide K chunk of the activation buffer: 32 samples x 128 bytes (hi [+ lo]) in this file's K-major form; the pair
+    // kernel's sample-contiguous form (fused_pair.cuh) pads it to X_HB
+    const int CH = (split ? 2 : 1) * (alias ? (int)X_HB : 32 * 128);
     p.x_chunks = (kmax + KCH - 1) / KCH;
     const TileSizes ts = tile_sizes(F, K, num, TS);
     size_t x = (size_t)p.x_chunks * CH;
