@@ -194,6 +194,15 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         for (int l = 0; l < L; ++l) {
             const int buf = l & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
             const bool last = (l == L - 1);
+            // bias / fc of this thread's neuron in both tiles: loaded before the wait, off the critical path
+            float bb2[2], ff2[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = (2 * j + (int)rank) * 128 + row;
+                const bool real = n < npad && n < N;
+                bb2[j] = real ? __ldg(p.bias[l] + n) : 0.f;
+                ff2[j] = (real && last) ? __ldg(p.fc + n) : 0.f;
+            }
             // the tile outputs overwrite the activation buffer the layer still reads: wait for every pair-tile of the layer
             for (int w = 0; w < PT; ++w) {
                 const int bit = buf * 2 + w;
@@ -209,9 +218,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 const int t = 2 * j + (int)rank;                    // this CTA's neuron tile of pair-tile j
                 const int n = t * 128 + row;
                 const int rows_valid = max(0, min(128, npad - t * 128));
-                const bool real = row < rows_valid && n < N;
-                const float bb = real ? __ldg(p.bias[l] + n) : 0.f;
-                const float ff = (real && last) ? __ldg(p.fc + n) : 0.f;
+                const float bb = bb2[j], ff = ff2[j];
                 FZ_PROG(8 + 4 * q + q4, (l << 16) | (j << 4) | (7 << 24));
                 const bool stamp = p.clk && threadIdx.x == 32 * EPI_WARP0 && l == 0;
                 if (stamp) FZ_CLK(40 + 4 * j);
@@ -261,7 +268,10 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 }
                 if (stamp) FZ_CLK(42 + 4 * j);
                 if (!last && t * 128 < npad) {
-                    asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");     // generic-proxy stores (local and peer) -> async proxy
+                    // generic-proxy stores -> async proxy (the tensor core of the CTA that holds them); the cluster-scope form costs
+                    // ~1.2 k cycles, the CTA-scope form ~50, so only the sets that stored into the peer pay for it
+                    if (half == (int)rank) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
                     if (stamp) FZ_CLK(43 + 4 * j);
                     tc_fence_before();
                     __syncwarp();
