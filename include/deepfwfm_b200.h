@@ -235,6 +235,29 @@ int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const fl
 int dfw_host_transport_is_mapped(const dfw_model* m, int precision, const void* xi_host, const void* xv_host,
                                  const void* logits_host, const void* prob_host);
 
+/* ---- one-shot magnitude pruning on the device -------------------------------
+ * Replaces the pruning block of fit (model/DeepFMs.py:647-673) applied once at the target rates, and its
+ * binary_search_threshold (model/DeepFMs.py:807-823), which costs up to 101 kernel + .item() round trips per tensor.  A set
+ * of device tensors (at most 2 * DFW_MAX_FIELDS) is treated as one concatenated array (the reference torch.cat's the
+ * fm_2nd_embeddings, :651-655). */
+typedef struct dfw_prune_span {
+    float* ptr;       /* device tensor, contiguous fp32 */
+    int64_t count;    /* elements                       */
+} dfw_prune_span;
+/* Bisection on t in [0, 100] until count(|w| < (float)t) / total is within 1e-4 of `target`, at most 101 probes -- the same
+ * fp64 steps as the Python loop, so *threshold_out (DEVICE double) equals the reference's return value bit for bit.  One
+ * cooperative launch, no host synchronisation.  sym_F > 0: `spans` is one (sym_F, sym_F) matrix R and the values are
+ * |0.5 (R + R^T)| (the field_cov recipe, :667-670).  probes_out (DEVICE int32) may be NULL.
+ * workspace: dfw_prune_workspace_bytes() bytes of device memory, 8-byte aligned. */
+size_t dfw_prune_workspace_bytes(void);
+int dfw_prune_threshold(const dfw_prune_span* spans, int n_spans, int sym_F, double target, int64_t total,
+                        void* workspace, size_t workspace_bytes, double* threshold_out, int32_t* probes_out, void* stream);
+/* w = 0 where |w| < (float)*threshold (DEVICE double) over every span (:660-666); sym_F > 0: R[i][j] = R[j][i] = 0 where
+ * |0.5 (R + R^T)[i][j]| < threshold (:671-673).  zeroed_out (DEVICE uint64, may be NULL) is incremented by the number of
+ * elements under the threshold.  Derived images (shallow image, bf16 / CSR weight images) must be rebuilt afterwards. */
+int dfw_prune_apply(const dfw_prune_span* spans, int n_spans, int sym_F, const double* threshold, uint64_t* zeroed_out,
+                    void* stream);
+
 /* ---- multi-GPU: row-sharded tables ------------------------------------------- */
 /* cudaMalloc'ed shard storage that can be exported to peers of the same node. */
 int dfw_shard_alloc(size_t bytes, void** dev_ptr);

@@ -52,6 +52,20 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert b"ABI mismatch" in lib.dfw_last_error_string()
 
 
+def test_prune_entry_points_check_arguments_before_touching_the_device(lib):
+    from xsdeepfwfm_deprecated_b200 import _lib
+    assert lib.dfw_prune_workspace_bytes() >= 64
+    span = (_lib.PruneSpan * 1)()
+    span[0].ptr, span[0].count = None, 10
+    assert lib.dfw_prune_threshold(None, 1, 0, 0.5, 10, None, 0, None, None, None) == -1          # NULL spans
+    assert lib.dfw_prune_threshold(span, 1, 0, 0.5, 10, None, 0, None, None, None) == -1          # NULL tensor with a count
+    assert lib.dfw_prune_threshold(span, 500, 0, 0.5, 10, None, 0, None, None, None) == -1        # too many spans
+    span[0].count = 0
+    assert lib.dfw_prune_threshold(span, 1, 7, 0.5, 49, None, 0, None, None, None) == -1          # sym needs F*F elements
+    assert lib.dfw_prune_apply(span, 1, 0, None, None, None) == -1                               # NULL threshold
+    assert b"threshold" in lib.dfw_last_error_string()
+
+
 def test_sass_is_sm100a_only():
     import subprocess
     from xsdeepfwfm_deprecated_b200 import _lib

@@ -487,3 +487,77 @@ def test_host_transports_mapped_and_staged_are_bit_identical():
         assert torch.equal(outs["mapped"][0], want), idt
         # the fp32 (staged-kernel) precision cannot use the mapped transport and says so
         assert lib.dfw_host_transport_is_mapped(plan.model_ref, _lib.PRECISIONS["fp32"], *args) == 0
+
+
+# ------------------------------------------------------------------------------- one-shot pruning on the device (8(f) row 3)
+def _prune_case(cfg, seed, sparse, emb_r, emb_corr, precision="bf16x3"):
+    w = synth.make_weights(cfg, seed=seed)
+    want = prune.one_shot_prune(w, sparse, emb_r, emb_corr)
+    m = to_cuda(cfg, w, precision=precision)
+    report = m.prune_one_shot(sparse=sparse, emb_r=emb_r, emb_corr=emb_corr)
+    got = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    return w, want, m, report, got
+
+
+def test_device_pruning_is_bit_identical_to_the_reference_recipe_config3():
+    """BASELINE config 3 at full size (1.33 M rows): thresholds equal to the reference bisection's doubles, every parameter
+    bit-identical to the reference recipe's output, the paper's census, and the pruned model's logits inside the fp32 bound."""
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w, want, m, report, got = _prune_case(cfg, 42, 0.9, 0.444, 1.0)
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    # thresholds: the device bisection takes the same fp64 steps as binary_search_threshold
+    stacked = np.concatenate([w[k] for k in w if "fm_2nd_embeddings" in k], axis=0)
+    assert report["emb"][0] == prune.bisect_threshold(stacked, 0.9 * 0.444, stacked.size)
+    for k in ("net_1_linear_1.weight", "net_1_linear_2.weight", "net_1_linear_3.weight", "fwfm_linear.weight"):
+        assert report[k][0] == prune.bisect_threshold(w[k], 0.9, w[k].size), k
+        assert report[k][2] == int((want[k] == 0).sum())
+    R = w["field_cov.weight"]
+    assert report["field_cov.weight"][0] == prune.bisect_threshold(np.float32(0.5) * (R + R.T), 0.9, R.size)
+    nz = sum(int((v != 0).sum()) for v in got.values())
+    assert abs(nz - 8_012_094) / 8_012_094 < 1e-3          # the paper's D-90 % & R-90 % & F-40 % parameter count
+    Xi, Xv = synth.make_inputs(cfg, 4096, seed=9, dist="zipf")
+    ref = closed_form.forward(cfg, want, Xi, Xv)["logit"]
+    for precision in ("bf16x3", "fp32_csr"):
+        m.precision = precision
+        assert np.abs(run(m, Xi, Xv) - ref).max() <= logit_tol(ref, FP32_REL), precision
+
+
+@pytest.mark.parametrize("name,sparse,emb_r,emb_corr", [("deepfwfm_fwlw", 0.5, 0.6, 0.7), ("qr_mult_fwlw", 0.9, 0.444, 1.0),
+                                                        ("deepfm", 0.3, 1.0, 1.0), ("twitter_shape", 0.95, 0.1, 0.5)])
+def test_device_pruning_matches_the_recipe_on_the_golden_models(name, sparse, emb_r, emb_corr):
+    """Other switch sets: QR tables (quotient and remainder tensors join the stacked embedding set), no fwfm_linear / no
+    field_cov (DeepFM), the Twitter shape; a CUDA tensor handed to binary_search_threshold takes the device path."""
+    c = load_case(name)
+    w = c["weights"]
+    want = prune.one_shot_prune(w, sparse, emb_r, emb_corr)
+    m = to_cuda(c["cfg"], w)
+    k0 = "net_1_linear_1.weight"
+    t_dev = m.binary_search_threshold(m.net_1_linear_1.weight.data, sparse, w[k0].size)
+    assert t_dev == prune.bisect_threshold(w[k0], sparse, w[k0].size)
+    m.prune_one_shot(sparse=sparse, emb_r=emb_r, emb_corr=emb_corr)
+    got = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    ref = closed_form.forward(c["cfg"], want, c["Xi"], c["Xv"])["logit"]
+    assert np.abs(run(m, c["Xi"], c["Xv"]) - ref).max() <= logit_tol(ref, FP32_REL)
+
+
+def test_device_pruning_edge_cases():
+    """Rates the bisection cannot meet (all-equal magnitudes: 101 probes, like the reference), an all-zero tensor, a tensor
+    whose storage is not 16-byte aligned, and the switches that leave parts untouched."""
+    m = to_cuda(*(lambda c: (c["cfg"], c["weights"]))(load_case("deepfwfm_fwlw")))
+    dev = m.bias.device
+    for t in (torch.full((1000,), 0.25, device=dev), torch.zeros(777, device=dev),
+              torch.randn(4099, device=dev)[3:], torch.randn(5, device=dev)):
+        a = t.detach().cpu().numpy()
+        for rate in (0.0, 0.5, 1.0):
+            assert m.binary_search_threshold(t, rate, a.size) == prune.bisect_threshold(a, rate, a.size), (a.size, rate)
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    rep = m.prune_one_shot(sparse=0.8, prune_fm=0, prune_r=0, prune_deep=1)
+    assert "emb" not in rep and "field_cov.weight" not in rep and "net_1_linear_2.weight" in rep
+    after = m.state_dict()
+    for k in before:
+        changed = not torch.equal(before[k], after[k])
+        assert changed == ("linear" in k and "weight" in k), k

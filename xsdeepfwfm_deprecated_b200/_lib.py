@@ -30,6 +30,10 @@ class FieldDesc(C.Structure):
                 ("w2_shard", C.c_void_p * DFW_MAX_RANKS)]
 
 
+class PruneSpan(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("count", C.c_int64)]
+
+
 class Csr(C.Structure):
     _fields_ = [("row_ptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
                 ("nnz", C.c_int32), ("max_row_nnz", C.c_int32)]
@@ -78,6 +82,9 @@ SYMBOLS = {
     "dfw_forward_host_stream_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_forward_host_stream": (C.c_int, [_MP, _vp, _vp, _i64, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp]),
     "dfw_host_transport_is_mapped": (C.c_int, [_MP, C.c_int, _vp, _vp, _vp, _vp]),
+    "dfw_prune_workspace_bytes": (_sz, []),
+    "dfw_prune_threshold": (C.c_int, [C.POINTER(PruneSpan), C.c_int, C.c_int, C.c_double, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "dfw_prune_apply": (C.c_int, [C.POINTER(PruneSpan), C.c_int, C.c_int, _vp, _vp, _vp]),
     "dfw_shard_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "dfw_shard_free": (C.c_int, [_vp]),
     "dfw_ipc_export": (C.c_int, [_vp, C.c_char_p]),

@@ -591,7 +591,12 @@ class DeepFMs(nn.Module):
         return (1.0 - cross_entropy / strawman) * 100.0
 
     def binary_search_threshold(self, param, target_percent, total_no):
-        """model/DeepFMs.py:807-823 (bisection on the magnitude threshold)."""
+        """model/DeepFMs.py:807-823 (bisection on the magnitude threshold).  A CUDA tensor is bisected on the device in one
+        cooperative launch (``dfw_prune_threshold``: same fp64 steps, same return value, one host read instead of up to 101);
+        a CPU tensor takes the reference's loop as is (host-side model surgery, not the forward path)."""
+        if isinstance(param, torch.Tensor) and param.is_cuda:
+            thr, _ = self._device_threshold([param.detach()], float(target_percent), int(total_no))
+            return float(thr.item())
         l, r = 0., 1e2
         cnt = 0
         mid = 0.
@@ -608,6 +613,66 @@ class DeepFMs(nn.Module):
             if cnt > 100:
                 break
         return mid
+
+    # ------------------------------------------------------------------ one-shot pruning on the device
+    @staticmethod
+    def _spans(tensors):
+        arr = (_lib.PruneSpan * len(tensors))()
+        for i, t in enumerate(tensors):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("pruning needs contiguous fp32 tensors")
+            arr[i].ptr, arr[i].count = t.data_ptr(), t.numel()
+        return arr
+
+    def _device_threshold(self, tensors, target, total, sym_F=0):
+        """(threshold, probes) as device tensors (fp64, int32) for the concatenation of `tensors`; no host synchronisation."""
+        lib = _lib.load()
+        dev = tensors[0].device
+        _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        ws = torch.empty(lib.dfw_prune_workspace_bytes(), dtype=torch.uint8, device=dev)
+        thr = torch.zeros(1, dtype=torch.float64, device=dev)
+        probes = torch.zeros(1, dtype=torch.int32, device=dev)
+        spans = self._spans(tensors)
+        with torch.cuda.device(dev):
+            _lib.check(lib.dfw_prune_threshold(spans, len(tensors), sym_F, target, total, ws.data_ptr(), ws.numel(),
+                                               thr.data_ptr(), probes.data_ptr(), _stream_ptr(dev)), "dfw_prune_threshold")
+        return thr, probes
+
+    def prune_one_shot(self, sparse=0.90, emb_r=1.0, emb_corr=1.0, prune_fm=1, prune_r=1, prune_deep=1):
+        """The pruning block of the reference's ``fit`` (model/DeepFMs.py:647-673) applied once at the full target rates, on
+        the device: one global threshold at rate ``sparse * emb_r`` over the concatenated ``fm_2nd_embeddings``, a per-tensor
+        threshold at rate ``sparse`` for every parameter whose name contains ``linear`` and ``weight`` (the MLP layers and
+        ``fwfm_linear``), and the symmetric mask ``|0.5 (R + R^T)| < t`` at rate ``sparse * emb_corr`` on ``field_cov.weight``.
+        Every threshold is bisected by one cooperative launch and applied by one more; nothing synchronises with the host until
+        the returned report is read.  Parameters are modified in place (zeros inside dense tensors, exactly what the
+        reference saves) and the derived images -- pair list of the pruned R, bf16 / CSR weight images -- are rebuilt on the
+        next forward.  Returns {name: (threshold, probes, zeroed)} with ``emb`` for the embedding set."""
+        lib = _lib.load()
+        dev = self.bias.device
+        if dev.type != "cuda":
+            raise RuntimeError("prune_one_shot runs on an sm_100 CUDA device (no CPU fallback); move the module first")
+        jobs = []          # (report name, tensors, sym_F, rate, total)
+        if prune_fm:
+            embs = [p_.data for n, p_ in self.named_parameters() if "fm_2nd_embeddings" in n]
+            total = sum(t.numel() for t in embs)
+            jobs.append(("emb", embs, 0, sparse * emb_r, total))
+        for n, p_ in self.named_parameters():
+            if "linear" in n and "weight" in n and prune_deep:
+                jobs.append((n, [p_.data], 0, sparse, p_.numel()))
+            if n == "field_cov.weight" and prune_r:
+                jobs.append((n, [p_.data], self.field_size, sparse * emb_corr, p_.numel()))
+        zeroed = torch.zeros(len(jobs), dtype=torch.int64, device=dev)
+        pending = []
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            for i, (name, tensors, sym_F, rate, total) in enumerate(jobs):
+                thr, probes = self._device_threshold(tensors, float(rate), int(total), sym_F)
+                _lib.check(lib.dfw_prune_apply(self._spans(tensors), len(tensors), sym_F, thr.data_ptr(),
+                                               zeroed[i:i + 1].data_ptr(), st), "dfw_prune_apply")
+                pending.append((name, thr, probes))
+        self.repack()
+        z = zeroed.cpu()
+        return {name: (float(thr.item()), int(probes.item()), int(z[i])) for i, (name, thr, probes) in enumerate(pending)}
 
     def predict(self, Xi, Xv):
         return self.predict_proba(Xi, Xv) > 0.5
