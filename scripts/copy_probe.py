@@ -29,3 +29,13 @@ def run(mode, ns):
 for mode in ("split", "merged", "xi_only"):
     for ns in (1, 3):
         run(mode, ns)
+# large-copy PCIe bandwidth for reference
+big_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); big_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for _ in range(2):
+    big_d.copy_(big_h, non_blocking=True)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    big_d.copy_(big_h, non_blocking=True)
+torch.cuda.synchronize()
+print(f"256 MiB H2D copies: {5 * (256 << 20) / (time.perf_counter() - t0) / 1e9:.1f} GB/s")

@@ -64,6 +64,33 @@ __global__ void gather_rows_kernel(const float* __restrict__ shard, int64_t shar
     }
 }
 
+// Mapped host transport, stage 1: a few small CTAs pull one batch's Xi / Xv from pinned host memory over PCIe into a device
+// staging slot (16-byte loads, two in flight per thread), ahead of the fused kernel that consumes it.  128 threads x 32
+// registers: such a CTA fits beside a resident fused CTA (640 x 96 registers), so the copy needs no SM of its own.
+__device__ __forceinline__ void pull_bytes(const void* __restrict__ src, void* __restrict__ dst, size_t bytes, uint32_t tid, uint32_t nth) {
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0) {
+        const uint4* s4 = static_cast<const uint4*>(src);
+        uint4* d4 = static_cast<uint4*>(dst);
+        const uint32_t n = (uint32_t)(bytes >> 4);       // a batch is far below 2^32 x 16 bytes
+        uint32_t i = tid;
+        for (; i + nth < n; i += 2 * nth) {
+            const uint4 a = s4[i], b = s4[i + nth];
+            d4[i] = a; d4[i + nth] = b;
+        }
+        if (i < n) d4[i] = s4[i];
+    } else {                                            // ragged tails / odd batch sizes: elements are 4 or 8 bytes wide
+        const uint32_t* s1 = static_cast<const uint32_t*>(src);
+        uint32_t* d1 = static_cast<uint32_t*>(dst);
+        for (size_t i = tid; i < (bytes >> 2); i += nth) d1[i] = s1[i];
+    }
+}
+__global__ void __launch_bounds__(128, 16) stage_inputs_kernel(const void* __restrict__ xi_src, void* __restrict__ xi_dst, size_t xi_bytes,
+                                                           const void* __restrict__ xv_src, void* __restrict__ xv_dst, size_t xv_bytes) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (xi_bytes) pull_bytes(xi_src, xi_dst, xi_bytes, tid, nth);
+    if (xv_bytes) pull_bytes(xv_src, xv_dst, xv_bytes, tid, nth);
+}
+
 }  // namespace dfw
 
 using namespace dfw;
@@ -198,11 +225,14 @@ extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, cons
 // .cuda() / .cpu() round trips.
 namespace {
 constexpr int kSlots = 3;      // staged transport: slots of the device workspace = streams in rotation
-constexpr int kLanes = 6;      // mapped transport: streams in rotation (no staging, so more of them cost nothing)
+constexpr int kLanes = 6;      // mapped transport: compute streams in rotation
+constexpr int kStage = 6;      // mapped transport: input staging slots (Xi + Xv of one batch each) at the front of the workspace
 struct HostPipe {
     cudaStream_t streams[kLanes] = {};
     cudaEvent_t done[kLanes] = {};
     cudaEvent_t start = nullptr;
+    cudaStream_t pull = nullptr;                    // high priority: the PCIe pull of batch i + 1 runs under the kernels of batch i
+    cudaEvent_t staged[kStage] = {}, freed[kStage] = {};
     int device = -1;
 };
 thread_local HostPipe g_pipe[8];
@@ -218,6 +248,13 @@ int get_pipe(HostPipe** out) {
             DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
         }
         DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.start, cudaEventDisableTiming));
+        int lo_prio = 0, hi_prio = 0;
+        DFW_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        DFW_CUDA_OK(cudaStreamCreateWithPriority(&hp.pull, cudaStreamNonBlocking, hi_prio));
+        for (int i = 0; i < kStage; ++i) {
+            DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.staged[i], cudaEventDisableTiming));
+            DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.freed[i], cudaEventDisableTiming));
+        }
         hp.device = dev;
     }
     *out = &hp;
@@ -236,12 +273,13 @@ void* mapped_alias(const void* host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-// 0 = choose (mapped when every buffer is device-visible and the fused kernel takes the model), 1 = staged copies, 2 = mapped
+// 0 = choose (mapped when every buffer is device-visible and the fused kernel takes the model), 1 = staged copies, 2 = mapped,
+// 3 = mapped without the pull stage (debug: the fused kernel's gather warps read Xi / Xv from host memory themselves)
 int host_transport_override() {
     static const int v = [] {
         const char* e = getenv("DFW_HOST_TRANSPORT");
         if (!e) return 0;
-        return !strcmp(e, "copy") ? 1 : !strcmp(e, "mapped") ? 2 : 0;
+        return !strcmp(e, "copy") ? 1 : !strcmp(e, "mapped") ? 2 : !strcmp(e, "mapped_direct") ? 3 : 0;
     }();
     return v;
 }
@@ -286,21 +324,45 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
     for (int i = 0; i < kLanes; ++i) DFW_CUDA_OK(cudaStreamWaitEvent(hp->streams[i], hp->start, 0));
     const size_t ib = (m->flags & DFW_XI_INT32) ? sizeof(int32_t) : sizeof(int64_t);
     if (dfw_host_transport_is_mapped(m, precision, xi_host, xv_host, logits_host, prob_host)) {
-        // Mapped transport: the host buffers are pinned, so the fused kernel loads each batch's indices / dense values and
-        // stores its results over PCIe itself -- the same bytes cross the bus, but there is one launch per batch, no copy-engine
-        // round trips and no staging; successive batches overlap on kLanes streams.
+        // Mapped transport: the host buffers are pinned, so kernels move the bytes over PCIe themselves -- no copy-engine round
+        // trips.  A small pull kernel on a high-priority stream brings batch i's Xi / Xv into a staging slot while earlier batches
+        // compute (a fused CTA that waited on PCIe for its indices would hold its SM idle); the fused kernel then gathers from
+        // HBM and its epilogue stores logits / probabilities straight into host memory.  Two launches per batch.
         const char* xi_d = static_cast<const char*>(mapped_alias(xi_host));
-        const float* xv_d = static_cast<const float*>(mapped_alias(xv_host));
+        const char* xv_d = static_cast<const char*>(mapped_alias(xv_host));
         float* logit_d = static_cast<float*>(mapped_alias(logits_host));
         float* prob_d = static_cast<float*>(mapped_alias(prob_host));
+        const bool direct = host_transport_override() == 3;
+        const size_t stage_bytes = H.oLogit;            // the Xi + Xv part of a slot
+        DFW_REQUIRE(direct || (size_t)kStage * stage_bytes <= workspace_bytes, DFW_E_WORKSPACE, "workspace too small for the staging slots");
+        if (!direct) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->start, 0));
         int64_t done = 0;
         for (int64_t i = 0; done < N; ++i, done += batch) {
             const int64_t b = N - done < batch ? N - done : batch;
-            if (int rc = dfw_forward_fused(m, reinterpret_cast<const int64_t*>(xi_d + (size_t)done * C * ib), C, 1,
-                                           xv_d ? xv_d + done * num : nullptr, num, 1, b, precision,
-                                           logit_d ? logit_d + done : nullptr, prob_d ? prob_d + done : nullptr, nullptr,
-                                           hp->streams[i % kLanes]))
+            cudaStream_t lane = hp->streams[i % kLanes];
+            const char* xi_src = xi_d + (size_t)done * C * ib;
+            const char* xv_src = xv_d ? xv_d + (size_t)done * num * sizeof(float) : nullptr;
+            const void* xi_in = xi_src;
+            const void* xv_in = xv_src;
+            const int slot = (int)(i % kStage);
+            if (!direct) {
+                char* ws = static_cast<char*>(workspace) + (size_t)slot * stage_bytes;
+                if (i >= kStage) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->freed[slot], 0));   // the slot's previous batch has been consumed
+                static const int pull_ctas = getenv("DFW_PULL_CTAS") ? atoi(getenv("DFW_PULL_CTAS")) : 64;   // 64 x 128 threads x 32 B in flight
+                stage_inputs_kernel<<<pull_ctas, 128, 0, hp->pull>>>(xi_src, ws + H.oXi, C > 0 ? (size_t)b * C * ib : 0,
+                                                              xv_src, ws + H.oXv, num > 0 ? (size_t)b * num * sizeof(float) : 0);
+                count_launch();
+                if (int rc = check_launch("stage_inputs_kernel")) return rc;
+                DFW_CUDA_OK(cudaEventRecord(hp->staged[slot], hp->pull));
+                DFW_CUDA_OK(cudaStreamWaitEvent(lane, hp->staged[slot], 0));
+                xi_in = ws + H.oXi;
+                xv_in = ws + H.oXv;
+            }
+            if (int rc = dfw_forward_fused(m, static_cast<const int64_t*>(xi_in), C, 1, static_cast<const float*>(xv_in), num, 1, b,
+                                           precision, logit_d ? logit_d + done : nullptr, prob_d ? prob_d + done : nullptr, nullptr,
+                                           lane))
                 return rc;
+            if (!direct) DFW_CUDA_OK(cudaEventRecord(hp->freed[slot], lane));
         }
         for (int i = 0; i < kLanes; ++i) {
             DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));
@@ -309,7 +371,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         DFW_CUDA_OK(cudaStreamSynchronize(main_st));
         return 0;
     }
-    DFW_REQUIRE(host_transport_override() != 2, DFW_E_UNSUPPORTED,
+    DFW_REQUIRE(host_transport_override() < 2, DFW_E_UNSUPPORTED,
                 "DFW_HOST_TRANSPORT=mapped, but a host buffer is not pinned or the fused kernel does not take this model");
     static const int dbg_skip = getenv("DFW_E2E_SKIP") ? atoi(getenv("DFW_E2E_SKIP")) : 0;   // debug: 1 = no H2D, 2 = no kernels
     int64_t done = 0;
