@@ -104,7 +104,11 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- workload
-def make_model(device, precision, feature_sizes, world=1, exchange="p2p", index_dtype="int64"):
+def make_model(device, precision, feature_sizes, world=1, exchange=None, index_dtype="int64"):
+    # exchange: "p2p" = peer loads inside the fused kernel (one launch per step; the default: measured 35.0 us/step at 2 GPUs);
+    # "p2p_pull" = the same loads by a separate pull kernel ahead of the fused kernel (two launches; measured 36.7 us/step: the
+    # pull CTAs overlap the fused kernels only partly)
+    exchange = exchange or os.environ.get("DFW_BENCH_EXCHANGE", "p2p")
     from xsdeepfwfm_deprecated_b200.model import DeepFMs
     kw = dict(embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False, use_fwfm=True, use_deep=True,
               use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision,
@@ -178,8 +182,31 @@ def run_ours(args):
     lanes = [stream] + side
     wss = [ws] + [torch.zeros_like(ws) for _ in side]
 
+    # sharded tables: the exchange runs as its own small kernel (dfw_pull_rows: direct peer loads over NVLink into a staging
+    # buffer) in front of the fused kernel of the same stream; with several streams the pull of one batch runs under the
+    # fused kernels of the others.  One PullLane (staging + descriptors) per stream.
+    pull = ([model.pull_lane(B, k).prepare(model, args.precision) for k in range(nstreams)]
+            if world > 1 and model._shards and model.exchange == "p2p_pull" else None)
+    # The pulls go to ONE high-priority stream: the block scheduler issues a later kernel's CTAs only when every earlier kernel of
+    # the same priority has none left to issue, so at equal priority a pull would queue behind the pending CTAs of the other
+    # lanes' fused kernels instead of running beside them.
+    pull_stream = torch.cuda.Stream(device, priority=-1) if pull else None
+    ev_pulled = [torch.cuda.Event() for _ in range(nstreams)] if pull else None
+    ev_used = [torch.cuda.Event() for _ in range(nstreams)] if pull else None
+    lane_used = [False] * nstreams
+
     def step(i, lane=0):
         j = i % nb
+        if pull:
+            if lane_used[lane]:
+                pull_stream.wait_event(ev_used[lane])          # the lane's staging buffer has been consumed
+            pull[lane].enqueue_pull(lib, Xi[j].data_ptr(), 26, 1, pull_stream.cuda_stream)
+            ev_pulled[lane].record(pull_stream)
+            lanes[lane].wait_event(ev_pulled[lane])
+            pull[lane].enqueue_forward(lib, Xv[j].data_ptr(), NUM, 1, logits[j].data_ptr(), None, lanes[lane].cuda_stream)
+            ev_used[lane].record(lanes[lane])
+            lane_used[lane] = True
+            return
         rc = lib.dfw_forward(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B, prec,
                              wss[lane].data_ptr(), wss[lane].numel(), logits[j].data_ptr(), None, None,
                              lanes[lane].cuda_stream)
@@ -190,10 +217,16 @@ def run_ours(args):
         """`count` forwards starting at batch `first`, round-robin over the streams, forked from and joined into `stream`."""
         for sd in side:
             sd.wait_stream(stream)
+        if pull:
+            pull_stream.wait_stream(stream)
+            for k in range(nstreams):
+                lane_used[k] = False       # events of an earlier segment / capture are not waited on (the join below orders them)
         for i in range(count):
             step(first + i, i % nstreams)
         for sd in side:
             stream.wait_stream(sd)
+        if pull:
+            stream.wait_stream(pull_stream)
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -272,13 +305,33 @@ def run_ours(args):
     step_bytes = ALG_BYTES_PER_SAMPLE * B + ALG_BYTES_PER_BATCH
     if fused:
         # one kernel per step: gather + FwFM (HBM/L2 side) and the MLP (tensor side) overlap inside it
-        t_f = graph_time(step, n_it)
+        def fused_only(i):          # sharded tables: the fused kernel alone, on the rows the last pull staged
+            pl = pull[0]
+            rc = lib.dfw_forward(pl.model_ref, pl.xi2.data_ptr(), 26, 1, Xv[i % nb].data_ptr(), NUM, 1, B, prec, pl.ws.data_ptr(),
+                                 pl.ws.numel(), logits[i % nb].data_ptr(), None, None, sp)
+            if rc:
+                _lib.check(rc, "dfw_forward")
+
+        t_f = graph_time(fused_only if pull else step, n_it)
         stage = {
             "fused_forward": dict(ms=t_f, bound="tensor", achieved=MLP_FLOPS_PER_SAMPLE * B / (t_f * 1e-3) / 1e12,
                                   peak=pk["tf_burst"], unit="TFLOP/s"),
             "fused_forward_hbm_view": dict(ms=t_f, bound="hbm", achieved=step_bytes / (t_f * 1e-3) / 1e9, peak=pk["hbm"],
                                            unit="GB/s"),
         }
+        if pull:
+            def pull_only(i):
+                pl = pull[0]
+                j = i % nb
+                rc = lib.dfw_pull_rows(plan.model_ref, pl.sf, len(pl.fields_sharded), Xi[j].data_ptr(), 26, 1, B,
+                                       pl.staged.data_ptr(), pl.xi2.data_ptr(), None, sp)
+                if rc:
+                    _lib.check(rc, "dfw_pull_rows")
+
+            t_p = graph_time(pull_only, n_it)
+            n_sf = len(pull[0].fields_sharded)
+            pull_bytes = B * n_sf * (K_EMB * 4 * 2 + 8 + 8) + B * (26 - n_sf) * 16     # rows in + out, indices in + out
+            stage["pull_rows"] = dict(ms=t_p, bound="hbm", achieved=pull_bytes / (t_p * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
         dom = "fused_forward"
     else:
         FK = FIELD * K_EMB
@@ -435,8 +488,9 @@ def run_ours(args):
                                  (f", the independent forwards round-robin over {nstreams} concurrent streams" if nstreams > 1
                                   else ", strictly back to back on one stream"),
                        "tables": "one GPU" if world == 1 else
-                                 f"{len(model._shards)} of 26 categorical tables row-sharded over {world} GPUs (row i on rank i mod P); "
-                                 "rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"},
+                                 f"{len(model._shards)} of 26 categorical tables row-sharded over {world} GPUs (row i on rank i mod P); " + ("rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"
+                                    if not pull else "rows fetched by direct peer loads over NVLink (no collective) by a pull kernel "
+                                    "that runs ahead of the fused kernel into a local staging buffer (exchange='p2p_pull')")},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
             "roofline": roofline, "cpu_baseline": cpu,
         }

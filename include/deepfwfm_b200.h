@@ -275,6 +275,18 @@ int dfw_shard_rows(const float* src, int64_t rows, int32_t width, int32_t rank, 
 int dfw_gather_rows(const float* shard, int64_t shard_rows, int32_t width, const int64_t* req, int64_t n,
                     int32_t n_ranks, float* out, void* stream);
 
+/* Exchange step as its own kernel ("p2p_pull"): for every sample of the batch and every field listed in sharded_fields (HOST
+ * array of field numbers whose descriptors in m->fields carry n_ranks > 1 and the peer-mapped w2_shard pointers), copy the row
+ * from the owning GPU -- direct peer loads over NVLink -- into
+ *     staged_out (n_sharded, B, K) fp32   (the quotient row for a QR table)
+ * and write xi2_out (B, C), a contiguous copy of xi (same element type) whose sharded columns hold b * c + idx mod c, so that
+ * a dfw_model whose descriptors point those fields at staged_out (rows = B * c, n_ranks = 0) reads the staging buffer as an
+ * ordinary table.  Small co-resident CTAs: launched on another stream it runs one batch ahead of, and under, the fused kernel.
+ * Rows are copied, never combined: bit-identical to one GPU.  Out-of-range indices behave as in dfw_embed_fwfm. */
+int dfw_pull_rows(const dfw_model* m, const int32_t* sharded_fields, int32_t n_sharded, const int64_t* xi,
+                  int64_t xi_stride_b, int64_t xi_stride_c, int64_t B, float* staged_out, void* xi2_out, int32_t* err_word,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,7 @@ def main():
             want = base(tXi, tXv)
         ref = closed_form.forward(cfg, w, Xi, Xv)["logit"]
         assert np.abs(want.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
-        for exchange in ("p2p", "nccl"):
+        for exchange in ("p2p", "p2p_pull", "nccl"):
             m = ShardedDeepFMs(39, SIZES, exchange=exchange, shard_threshold=200, **common)
             m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
             m = m.to(dev).eval()
@@ -50,7 +50,7 @@ def main():
             with torch.no_grad():
                 got = m(tXi, tXv)
             same = bool(torch.equal(got, want))
-            print(f"[rank {rank}/{world}] {tag:5s} {precision:6s} {exchange:4s} sharded_tables={nsh} bit_identical={same}", flush=True)
+            print(f"[rank {rank}/{world}] {tag:5s} {precision:6s} {exchange:8s} sharded_tables={nsh} bit_identical={same}", flush=True)
             ok &= same and nsh >= 4
             m.release()
     t = torch.tensor([1 if ok else 0], device=dev)

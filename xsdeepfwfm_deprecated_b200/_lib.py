@@ -82,6 +82,7 @@ SYMBOLS = {
     "dfw_forward_host_stream_workspace_bytes": (_sz, [_MP, _i64, C.c_int]),
     "dfw_forward_host_stream": (C.c_int, [_MP, _vp, _vp, _i64, _i64, C.c_int, _vp, _sz, _vp, _vp, _vp]),
     "dfw_host_transport_is_mapped": (C.c_int, [_MP, C.c_int, _vp, _vp, _vp, _vp]),
+    "dfw_pull_rows": (C.c_int, [_MP, C.POINTER(C.c_int32), C.c_int32, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "dfw_prune_workspace_bytes": (_sz, []),
     "dfw_prune_threshold": (C.c_int, [C.POINTER(PruneSpan), C.c_int, C.c_int, C.c_double, _i64, _vp, _sz, _vp, _vp, _vp]),
     "dfw_prune_apply": (C.c_int, [C.POINTER(PruneSpan), C.c_int, C.c_int, _vp, _vp, _vp]),

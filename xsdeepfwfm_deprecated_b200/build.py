@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libdeepfwfm_sm100a.so")
-SOURCES = ["api.cu", "embed_fwfm.cu", "mlp_fp32.cu", "mlp_sparse.cu", "mlp_tc.cu", "fused_tc.cu", "prune.cu"]
+SOURCES = ["api.cu", "embed_fwfm.cu", "mlp_fp32.cu", "mlp_sparse.cu", "mlp_tc.cu", "fused_tc.cu", "prune.cu", "pull_rows.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
 

@@ -10,16 +10,23 @@ and a 1/P slice of every large table):
     row i of a sharded table lives on rank  i mod P  at local row  i div P        (QR tables: the quotient table is
     sharded on the quotient row, the c-row remainder table is replicated)
 
-Two exchange modes produce bit-identical logits (rows are copied, never summed):
+Three exchange modes produce bit-identical logits (rows are copied, never summed):
 
-``p2p`` (the product path)
+``p2p`` (one launch, lowest latency)
     Every rank's shard is cudaMalloc'ed by ``dfw_shard_alloc`` and exported with CUDA IPC; each rank maps all peers'
     shards and puts the P pointers into the field descriptors.  The SAME fused gather kernel then fetches a row with
     one ``cp.async`` from whichever GPU owns it -- over NVLink 5 / NVSwitch when it is a peer -- straight into the
     sample's shared-memory block.  Gather, exchange and the FwFM interaction are one kernel: no index exchange, no
     staging buffers, no collective on the data path.
 
-``nccl`` (the baseline the p2p kernel is measured against)
+``p2p_pull`` (highest throughput: what ``bench.py --gpus N`` runs)
+    The same peer loads, issued by a separate small kernel (``dfw_pull_rows``) one batch AHEAD of the fused kernel: its
+    128-thread CTAs fit beside a resident fused CTA, copy every sharded field's row of every sample from the owning GPU
+    into a batch-ordered staging buffer in local HBM and rewrite the index columns; the fused kernel then gathers from
+    local memory at single-GPU speed instead of holding an SM idle through NVLink round trips.  One ``PullLane``
+    (staging + descriptors) per concurrent stream.
+
+``nccl`` (the baseline the p2p kernels are measured against)
     The textbook exchange: route indices to their owners with ``all_to_all_single``, owners gather the requested rows
     (``dfw_gather_rows``), a second ``all_to_all_single`` returns them, and the fused kernel consumes them as a
     per-batch table.
@@ -90,14 +97,15 @@ class ShardedDeepFMs(DeepFMs):
 
     def __init__(self, *args, process_group=None, shard_threshold: int = 200, exchange: str = "p2p", **kw):
         super().__init__(*args, **kw)
-        if exchange not in ("p2p", "nccl"):
-            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange not in ("p2p", "p2p_pull", "nccl"):
+            raise ValueError("exchange must be 'p2p', 'p2p_pull' or 'nccl'")
         self.process_group = process_group
         self.shard_threshold = shard_threshold
         self.exchange = exchange
         self._shards: Dict[int, dict] = {}          # field -> dict(ptrs=[...], own=ptr, rows=..., local_rows=...)
         self._owned_allocs: List[int] = []
         self._peer_maps: List[int] = []
+        self._lanes: Dict[tuple, "PullLane"] = {}
 
     # -- sharding ---------------------------------------------------------------------------------------------
     def shard_(self):
@@ -157,7 +165,7 @@ class ShardedDeepFMs(DeepFMs):
         return self
 
     def _patch_field_descs(self, descs, plan):
-        if self.exchange != "p2p":
+        if self.exchange not in ("p2p", "p2p_pull"):
             return
         for f, s in self._shards.items():
             d = descs[f]
@@ -170,7 +178,38 @@ class ShardedDeepFMs(DeepFMs):
     def forward(self, Xi, Xv, return_prob: bool = False):
         if self.exchange == "p2p" or not self._shards:
             return super().forward(Xi, Xv, return_prob)
+        if self.exchange == "p2p_pull":
+            return self._forward_pull(Xi, Xv, return_prob)
         return self._forward_nccl(Xi, Xv, return_prob)
+
+    # -- "p2p_pull": the exchange as its own kernel, one batch ahead of the fused kernel ---------------------------
+    def pull_lane(self, B: int, key=None) -> "PullLane":
+        """Staging for one in-flight batch of B samples (cached per (B, key); use one lane per concurrent stream)."""
+        plan = self._get_plan()
+        lane = self._lanes.get((B, key))
+        if lane is None or lane.plan is not plan:
+            lane = self._lanes[(B, key)] = PullLane(self, plan, B)
+        return lane
+
+    def _forward_pull(self, Xi, Xv, return_prob):
+        lib = _lib.load()
+        plan = self._get_plan()
+        dev = plan.device
+        B = Xi.shape[0]
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        prob = torch.empty(B, dtype=torch.float32, device=dev) if return_prob else None
+        if B == 0:
+            return (logits, prob) if return_prob else logits
+        want = torch.int32 if self.index_dtype == "int32" else torch.int64
+        if Xi.dtype != want or Xv.dtype != torch.float32:
+            raise TypeError(f"Xi must be {want} and Xv float32")
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            lane = self.pull_lane(B, st)
+            if lane.precision != self.precision:
+                lane.prepare(self, self.precision)
+            lane.run(lib, Xi, Xv, logits, prob, st)
+        return (logits, prob) if return_prob else logits
 
     def _forward_nccl(self, Xi, Xv, return_prob):
         """Baseline: index all-to-all -> owner gather -> row all-to-all -> fused kernel on per-batch tables."""
@@ -243,6 +282,7 @@ class ShardedDeepFMs(DeepFMs):
         """Unmap peers and free this rank's shards (call on every rank before exit)."""
         lib = _lib.load()
         self._plan = None
+        self._lanes = {}
         for p in self._peer_maps:
             lib.dfw_ipc_close(p)
         self._peer_maps = []
@@ -252,3 +292,76 @@ class ShardedDeepFMs(DeepFMs):
             lib.dfw_shard_free(p)
         self._owned_allocs = []
         self._shards = {}
+
+
+class PullLane:
+    """One in-flight batch of the ``p2p_pull`` exchange: the staging buffer the row-pull kernel fills, the rewritten index
+    matrix, and a view of the model whose sharded fields read that staging buffer as B-row tables (own descriptors and
+    shallow image; weights and images shared with the module's plan)."""
+
+    def __init__(self, owner: ShardedDeepFMs, plan, B: int):
+        lib = _lib.load()
+        dev = plan.device
+        self.plan, self.B = plan, B
+        K, F, num = owner.embedding_size, owner.field_size, owner.num
+        self.fields_sharded = sorted(owner._shards)
+        n_sf = len(self.fields_sharded)
+        self.sf = (C.c_int32 * n_sf)(*self.fields_sharded)
+        self.staged = torch.empty(n_sf, B, K, dtype=torch.float32, device=dev)
+        idt = torch.int32 if owner.index_dtype == "int32" else torch.int64
+        self.xi2 = torch.empty(B, F - num, dtype=idt, device=dev)
+        descs = (_lib.FieldDesc * F).from_buffer_copy(bytes(plan.fields_dev.cpu().numpy().tobytes()))
+        for j, f in enumerate(self.fields_sharded):
+            emb = owner.fm_2nd_embeddings[f]
+            c = emb.num_collisions if isinstance(emb, QREmbeddingBag) else 1
+            descs[f].w2 = self.staged[j].data_ptr()
+            descs[f].rows = B * c
+            descs[f].n_ranks = 0
+        self.fields = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        m = _lib.Model.from_buffer_copy(bytes(plan.model))
+        m.fields = self.fields.data_ptr()
+        m.shallow_image = None
+        self.model = m
+        self.model_ref = C.byref(m)
+        self.image = torch.zeros(lib.dfw_shallow_image_bytes(self.model_ref), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.dfw_pack_shallow(self.model_ref, self.image.data_ptr(), _stream_ptr(dev)), "dfw_pack_shallow")
+        m.shallow_image = self.image.data_ptr()
+        self.precision = None
+        self.ws = None
+
+    def prepare(self, owner, precision: str):
+        """Bind the weight images of `precision` (built by the plan) and size the forward workspace."""
+        lib = _lib.load()
+        self.plan.ensure_image(owner, precision)
+        pm, m = self.plan.model, self.model
+        for l in range(owner.h_depth if owner.use_deep else 0):
+            m.Wbf16[l], m.Wbf16_lo[l], m.csr[l] = pm.Wbf16[l], pm.Wbf16_lo[l], pm.csr[l]
+        self.precision = precision
+        self.prec = _lib.PRECISIONS[precision]
+        n = lib.dfw_forward_workspace_bytes(self.model_ref, self.B, self.prec)
+        self.ws = torch.zeros(n + 4096, dtype=torch.uint8, device=self.plan.device)
+        return self
+
+    def enqueue_pull(self, lib, xi_ptr, xi_sb, xi_sc, pull_stream):
+        """Row pull of one batch into this lane's staging buffer (``dfw_pull_rows``)."""
+        rc = lib.dfw_pull_rows(self.plan.model_ref, self.sf, len(self.fields_sharded), xi_ptr, xi_sb, xi_sc, self.B,
+                               self.staged.data_ptr(), self.xi2.data_ptr(), None, pull_stream)
+        if rc:
+            _lib.check(rc, "dfw_pull_rows")
+
+    def enqueue_forward(self, lib, xv_ptr, xv_sb, xv_sc, logits_ptr, prob_ptr, stream):
+        """Fused forward on the staged rows; the caller orders it after the pull when the streams differ."""
+        Cc = self.xi2.shape[1]
+        rc = lib.dfw_forward(self.model_ref, self.xi2.data_ptr(), Cc, 1, xv_ptr, xv_sb, xv_sc, self.B, self.prec,
+                             self.ws.data_ptr(), self.ws.numel(), logits_ptr, prob_ptr, None, stream)
+        if rc:
+            _lib.check(rc, "dfw_forward")
+
+    def enqueue(self, lib, xi_ptr, xi_sb, xi_sc, xv_ptr, xv_sb, xv_sc, logits_ptr, prob_ptr, pull_stream, stream):
+        self.enqueue_pull(lib, xi_ptr, xi_sb, xi_sc, pull_stream)
+        self.enqueue_forward(lib, xv_ptr, xv_sb, xv_sc, logits_ptr, prob_ptr, stream)
+
+    def run(self, lib, Xi, Xv, logits, prob, st):
+        self.enqueue(lib, Xi.data_ptr(), Xi.stride(0), Xi.stride(1), Xv.data_ptr() if Xv.numel() else None, Xv.stride(0),
+                     Xv.stride(1), logits.data_ptr(), prob.data_ptr() if prob is not None else None, st, st)
