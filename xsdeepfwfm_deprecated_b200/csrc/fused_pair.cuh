@@ -13,16 +13,20 @@
 //               (cp.async.bulk.tensor ... cta_group::2), which expects both boxes
 //   warps 2-3   MMA issuers (leader only), one per ring: tcgen05.mma.cta_group::2, M = 256, N = 64, K = 16, K-outer order;
 //               tcgen05.commit ... multicast releases the stage in both CTAs and signals both CTAs' acc_full
-//   warps 4-7 / 8-11  epilogue: thread = neuron (TMEM lane) of this CTA's tile; warps 4-7 take sample columns 0..31 (CTA 0's
-//               samples), warps 8-11 (gather warps once their interaction is done) columns 32..63 (CTA 1's samples); the bf16
-//               (hi | lo) activations go straight into the activation buffer of the CTA that owns the samples -- st.shared::cluster
-//               to the peer -- and the leader's act_ready barrier of the tile gets one arrive per warp (remote from CTA 1)
+//   epilogue    four sets of four warps (4-7, 8-11, 12-15, 16-19; warp % 4 = TMEM lane quarter, thread = neuron of this CTA's tile):
+//               set q takes sample columns 16 q .. 16 q + 15 (the samples of CTA q / 2) of pair-tile 0, then of pair-tile 1, so
+//               the next layer's first operand chunks are ready after half of the epilogue work.  The bf16 (hi | lo) activations
+//               go straight into the activation buffer of the CTA that owns the samples as 16-byte stores (sample-contiguous
+//               operand, see X_SBO below) -- st.shared::cluster to the peer -- and the leader's act_ready barrier of the tile
+//               gets one arrive per warp (remote from CTA 1).  Sets B-D are the gather warps once their interaction is done.
 //   warps 8-17  gather group: as in fused_tc.cu (register path); x_ready is the leader's barrier, 10 arrives from each CTA
-//   last layer  every warp reduces its 32 neurons x 32 samples to per-sample sums and stores them into the owner CTA's
+//   last layer  every warp reduces its 32 neurons x 16 samples to per-sample sums and stores them into the owner CTA's
 //               `red` array; the owner adds them to its shallow part
 //
-//   bf16x3: three N = 64 MMAs per k-step into the same 64 accumulator columns -- W_hi X_hi, W_hi X_lo (B descriptor + 32 rows),
-//   W_lo X_hi -- because the stacked-N trick of fused_tc.cu would interleave the two CTAs' hi/lo columns.
+//   bf16x3: three N = 64 MMAs per k-step into the same 64 accumulator columns -- W_hi X_hi, W_hi X_lo (B descriptor + X_HB),
+//   W_lo X_hi.  One N = 128 MMA on [X_hi | X_lo] would read the weights once for two products (measured: -15 % MMA time), but the
+//   third product then lands on different accumulator columns for the two CTAs' samples, i.e. a sample's rounding would depend on
+//   its position in the batch; the tests pin batch-order equivariance, so it is not used.
 //   One wave only (every tile owned by exactly one CTA of the grid); larger batches use fused_tc.cu.
 #pragma once
 #include "fused_common.cuh"
@@ -35,7 +39,7 @@ struct PairBars {
     uint64_t empty[2][RING_MAX];     // per CTA: stage s consumed (multicast commit of the leader)
     uint64_t x_ready;                // leader: layer-1 operand written in both CTAs (2 x G_WARPS arrives)
     uint64_t shallow_ready;          // per CTA
-    uint64_t act_ready[2][MAX_MT];   // leader: [layer parity][neuron tile] 8 arrives from the CTA that owns the tile
+    uint64_t act_ready[2][MAX_MT];   // leader: [layer parity][neuron tile] 16 arrives (4 sets x 4 warps) from the CTA that owns the tile
     uint64_t acc_full[2][2];         // per CTA: [layer parity][pair-tile] accumulators complete (multicast commit)
     uint64_t fin;                    // per CTA: the 8 partial-sum blocks of its samples are in `red`
     uint32_t tmem_holder, pad_;

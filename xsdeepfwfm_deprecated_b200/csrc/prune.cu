@@ -226,9 +226,11 @@ extern "C" int dfw_prune_threshold(const dfw_prune_span* spans, int n_spans, int
     DFW_REQUIRE(per_sm >= 1, DFW_E_UNSUPPORTED, "bisect_kernel does not fit an SM");
     int64_t elems = 0;
     for (int i = 0; i < n_spans; ++i) elems += spans[i].count;
-    // one CTA per SM, fewer for small tensors (a CTA should have at least ~4 K elements to count)
+    // a persistent grid of up to 4 CTAs per SM (the probes of an L2-resident tensor are latency-bound: bytes in flight matter),
+    // fewer for small tensors (a CTA should have at least ~4 K elements to count); all CTAs must be co-resident
+    const int cap = sms * (per_sm < 4 ? per_sm : 4);
     long long want = (elems + 4095) / 4096;
-    const int grid = (int)(want < 1 ? 1 : (want > sms ? sms : want));
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     DFW_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(pr::State), st));
     pr::State* state = static_cast<pr::State*>(workspace);
     long long total_ll = total;
