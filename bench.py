@@ -31,10 +31,38 @@ import torch  # noqa: E402
 
 METRIC = "DeepFwFM inference samples/sec"
 UNIT = "samples/s"
-FIELD, NUM, K_EMB, NODES, DEPTH = 39, 13, 10, 400, 3
-ALG_BYTES_PER_SAMPLE = 26 * 8 + 13 * 4 + 26 * K_EMB * 4 + 4          # 1304
-ALG_BYTES_PER_BATCH = 477600 * 4 + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4   # weights read once per launch
-MLP_FLOPS_PER_SAMPLE = 2 * (390 * 400 + 2 * 400 * 400 + 400)          # 952,800
+K_EMB, NODES, DEPTH = 10, 400, 3
+FIELD = NUM = CATS = 0
+SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT = None, {}, "", False
+ALG_BYTES_PER_SAMPLE = ALG_BYTES_PER_BATCH = MLP_FLOPS_PER_SAMPLE = 0
+
+
+def set_workload(name):
+    """criteo = BASELINE config 2 (the headline); criteo_qr = config 4(ii); twitter = config 5's shape (supplementary lines)."""
+    global FIELD, NUM, CATS, SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT, ALG_BYTES_PER_SAMPLE, ALG_BYTES_PER_BATCH, MLP_FLOPS_PER_SAMPLE
+    from oracle import synth
+    if name == "criteo":
+        FIELD, NUM, SIZES, MODEL_KW = 39, 13, synth.CRITEO_PAPER, {}
+        WORKLOAD_TEXT = ("BASELINE config 2: DeepFwFM dense (fwfm+deep+fwlw), F=39 (13 numeric), K=10, MLP 400x400x400, "
+                         "paper-Criteo cardinalities (1.33 M rows, 53 MB fp32), uniform indices")
+    elif name == "criteo_qr":
+        FIELD, NUM, SIZES = 39, 13, synth.CRITEO_KAGGLE
+        MODEL_KW = dict(embedding_bag=1, qr_flag=1, qr_operation="mult", qr_collisions=4, qr_threshold=200)
+        WORKLOAD_TEXT = ("BASELINE config 4(ii): DeepFwFM with QREmbeddingBag (mult, c=4, threshold 200) on the un-thresholded "
+                         "Kaggle cardinalities (33.8 M categories -> 8.44 M quotient rows, 338 MB fp32), F=39, K=10, MLP "
+                         "400x400x400, uniform indices")
+    elif name == "twitter":
+        FIELD, NUM, SIZES, MODEL_KW, XV_UNIT = 47, 11, synth.TWITTER_SYNTH, {}, True
+        WORKLOAD_TEXT = ("BASELINE config 5 shape: DeepFwFM dense (fwfm+deep+fwlw), Twitter RecSys2020 layout F=47 (11 numeric, "
+                         "36 categorical), K=10, MLP 400x400x400, synthetic cardinalities (69.2 M rows, 2.77 GB fp32), uniform indices")
+    else:
+        raise ValueError(name)
+    CATS = FIELD - NUM
+    FK = FIELD * K_EMB
+    mlp_params = FK * NODES + NODES + (DEPTH - 1) * (NODES * NODES + NODES) + NODES
+    ALG_BYTES_PER_SAMPLE = CATS * 8 + NUM * 4 + CATS * K_EMB * 4 + 4          # Criteo: 1304, Twitter: 1776 (SURVEY 8(d))
+    ALG_BYTES_PER_BATCH = mlp_params * 4 + FIELD * FIELD * 4 + FIELD * K_EMB * 4 + NUM * K_EMB * 4   # read once per launch
+    MLP_FLOPS_PER_SAMPLE = 2 * (FK * NODES + (DEPTH - 1) * NODES * NODES + NODES)                    # Criteo: 952,800
 
 
 def parse():
@@ -44,6 +72,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--workload", default="criteo", choices=["criteo", "criteo_qr", "twitter"],
+                    help="criteo = BASELINE config 2 (the headline line); the others are supplementary shapes")
     ap.add_argument("--precision", default=os.environ.get("DFW_BENCH_PRECISION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32", "fp32_csr"])
     ap.add_argument("--nbatches", type=int, default=256, help="distinct input batches cycled (> L2 in total)")
@@ -112,7 +142,7 @@ def make_model(device, precision, feature_sizes, world=1, exchange=None, index_d
     from xsdeepfwfm_deprecated_b200.model import DeepFMs
     kw = dict(embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False, use_fwfm=True, use_deep=True,
               use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision,
-              index_dtype=index_dtype)
+              index_dtype=index_dtype, **MODEL_KW)
     if world > 1:
         from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
         m = ShardedDeepFMs(FIELD, feature_sizes, exchange=exchange, shard_threshold=200, **kw)
@@ -121,8 +151,9 @@ def make_model(device, precision, feature_sizes, world=1, exchange=None, index_d
     m = m.to(device)
     m.init_weights()                       # the reference's init distributions, on the device
     with torch.no_grad():
-        for f in range(FIELD):
-            m.fm_2nd_embeddings[f].weight.mul_(10.0)      # trained-scale embeddings
+        for n_, p_ in m.named_parameters():
+            if "fm_2nd_embeddings" in n_ and not n_.endswith("weight_r"):
+                p_.mul_(10.0)                              # trained-scale embeddings
     if world > 1:
         m.shard_()          # every rank built identical full tables (same seed); keep only this rank's rows
     return m.eval().freeze()
@@ -135,7 +166,10 @@ def make_batches(device, feature_sizes, B, nb, seed):
     u = torch.rand(nb, B, FIELD - NUM, generator=g, device=device, dtype=torch.float64)
     Xi = (u * cats).long().clamp_(max=int(max(feature_sizes)) - 1)
     Xi = torch.minimum(Xi, (cats - 1).long()).unsqueeze(-1).contiguous()        # (nb, B, 26, 1) uniform indices
-    Xv = torch.randint(0, 50, (nb, B, NUM), generator=g, device=device).float()
+    if XV_UNIT:     # Twitter: MinMax-scaled dense features (data/large/preprocess_twitter.py:102-103)
+        Xv = torch.rand(nb, B, NUM, generator=g, device=device)
+    else:
+        Xv = torch.randint(0, 50, (nb, B, NUM), generator=g, device=device).float()
     return Xi, Xv
 
 
@@ -162,7 +196,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
-    sizes = synth.CRITEO_PAPER
+    sizes = SIZES
     B, nb = args.batch, args.nbatches
     model = make_model(device, args.precision, sizes, world)
     Xi, Xv = make_batches(device, sizes, B, nb, seed=rank)
@@ -200,14 +234,14 @@ def run_ours(args):
         if pull:
             if lane_used[lane]:
                 pull_stream.wait_event(ev_used[lane])          # the lane's staging buffer has been consumed
-            pull[lane].enqueue_pull(lib, Xi[j].data_ptr(), 26, 1, pull_stream.cuda_stream)
+            pull[lane].enqueue_pull(lib, Xi[j].data_ptr(), CATS, 1, pull_stream.cuda_stream)
             ev_pulled[lane].record(pull_stream)
             lanes[lane].wait_event(ev_pulled[lane])
             pull[lane].enqueue_forward(lib, Xv[j].data_ptr(), NUM, 1, logits[j].data_ptr(), None, lanes[lane].cuda_stream)
             ev_used[lane].record(lanes[lane])
             lane_used[lane] = True
             return
-        rc = lib.dfw_forward(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B, prec,
+        rc = lib.dfw_forward(plan.model_ref, Xi[j].data_ptr(), CATS, 1, Xv[j].data_ptr(), NUM, 1, B, prec,
                              wss[lane].data_ptr(), wss[lane].numel(), logits[j].data_ptr(), None, None,
                              lanes[lane].cuda_stream)
         if rc:
@@ -307,7 +341,7 @@ def run_ours(args):
         # one kernel per step: gather + FwFM (HBM/L2 side) and the MLP (tensor side) overlap inside it
         def fused_only(i):          # sharded tables: the fused kernel alone, on the rows the last pull staged
             pl = pull[0]
-            rc = lib.dfw_forward(pl.model_ref, pl.xi2.data_ptr(), 26, 1, Xv[i % nb].data_ptr(), NUM, 1, B, prec, pl.ws.data_ptr(),
+            rc = lib.dfw_forward(pl.model_ref, pl.xi2.data_ptr(), CATS, 1, Xv[i % nb].data_ptr(), NUM, 1, B, prec, pl.ws.data_ptr(),
                                  pl.ws.numel(), logits[i % nb].data_ptr(), None, None, sp)
             if rc:
                 _lib.check(rc, "dfw_forward")
@@ -323,14 +357,14 @@ def run_ours(args):
             def pull_only(i):
                 pl = pull[0]
                 j = i % nb
-                rc = lib.dfw_pull_rows(plan.model_ref, pl.sf, len(pl.fields_sharded), Xi[j].data_ptr(), 26, 1, B,
+                rc = lib.dfw_pull_rows(plan.model_ref, pl.sf, len(pl.fields_sharded), Xi[j].data_ptr(), CATS, 1, B,
                                        pl.staged.data_ptr(), pl.xi2.data_ptr(), None, sp)
                 if rc:
                     _lib.check(rc, "dfw_pull_rows")
 
             t_p = graph_time(pull_only, n_it)
             n_sf = len(pull[0].fields_sharded)
-            pull_bytes = B * n_sf * (K_EMB * 4 * 2 + 8 + 8) + B * (26 - n_sf) * 16     # rows in + out, indices in + out
+            pull_bytes = B * n_sf * (K_EMB * 4 * 2 + 8 + 8) + B * (CATS - n_sf) * 16     # rows in + out, indices in + out
             stage["pull_rows"] = dict(ms=t_p, bound="hbm", achieved=pull_bytes / (t_p * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
         dom = "fused_forward"
     else:
@@ -345,7 +379,7 @@ def run_ours(args):
 
         def embed(i):
             j = i % nb
-            rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), NUM, 1, B,
+            rc = lib.dfw_embed_fwfm(plan.model_ref, Xi[j].data_ptr(), CATS, 1, Xv[j].data_ptr(), NUM, 1, B,
                                     None if bf else E.data_ptr(), ldE, Eb.data_ptr() if bf else None, ldEb,
                                     shallow.data_ptr(), None, sp)
             if rc:
@@ -366,7 +400,7 @@ def run_ours(args):
             torch.cuda.synchronize(device)
         t_embed = graph_time(embed, n_it)
         t_mlp = graph_time(mlp, n_it)
-        embed_bytes = ALG_BYTES_PER_SAMPLE * B + 39 * 39 * 4 + 39 * K_EMB * 4 + 13 * K_EMB * 4
+        embed_bytes = ALG_BYTES_PER_SAMPLE * B + FIELD * FIELD * 4 + FIELD * K_EMB * 4 + NUM * K_EMB * 4
         stage = {
             "embed_fwfm": dict(ms=t_embed, bound="hbm", achieved=embed_bytes / (t_embed * 1e-3) / 1e9, peak=pk["hbm"],
                                unit="GB/s"),
@@ -377,7 +411,7 @@ def run_ours(args):
     d = stage[dom]
     traffic = None      # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if fused and B == 4096 and os.path.exists(tpath):
+    if fused and B == 4096 and args.workload == "criteo" and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.precision)
     roofline = dict(kernel=dom, bound=d["bound"], achieved=round(d["achieved"], 3), peak=d["peak"], unit=d["unit"],
                     frac=round(d["achieved"] / d["peak"], 5), traffic=traffic, peak_source=pk["src"],
@@ -390,7 +424,7 @@ def run_ours(args):
     # every step's Xi/Xv start in pinned host memory and its probabilities end there: H2D -> kernel(s) -> sigmoid -> D2H per
     # batch on rotating streams (copies overlap kernels), one host synchronisation per call of `nh` steps
     nh = max(1, min(64, args.steps))
-    hXi = torch.empty(nh, B, 26, dtype=torch.int64).pin_memory()
+    hXi = torch.empty(nh, B, CATS, dtype=torch.int64).pin_memory()
     hXv = torch.empty(nh, B, NUM, dtype=torch.float32).pin_memory()
     hXi.copy_(Xi[:nh, :, :, 0].cpu()); hXv.copy_(Xv[:nh].cpu())
     hout = torch.empty(nh, B, dtype=torch.float32).pin_memory()
@@ -423,7 +457,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e = dict(value=round(world * B * args.steps / t_e2e, 1), unit=UNIT,
-               h2d_bytes_per_step=B * (26 * 8 + NUM * 4), d2h_bytes_per_step=B * 4,
+               h2d_bytes_per_step=B * (CATS * 8 + NUM * 4), d2h_bytes_per_step=B * 4,
                ms_per_step=round(t_e2e / args.steps * 1e3, 4),
                transport="mapped" if mapped else "staged",
                api=("dfw_forward_host_stream, mapped transport: every step's Xi/Xv are loaded from pinned host memory over "
@@ -461,7 +495,7 @@ def run_ours(args):
             torch.cuda.synchronize(device)
             t32 = time.perf_counter() - t0
             e2e["int32_indices"] = dict(value=round(B * args.steps / t32, 1), unit=UNIT,
-                                        h2d_bytes_per_step=B * (26 * 4 + NUM * 4), ms_per_step=round(t32 / args.steps * 1e3, 4))
+                                        h2d_bytes_per_step=B * (CATS * 4 + NUM * 4), ms_per_step=round(t32 / args.steps * 1e3, 4))
             del m32
         except Exception as ex:        # supplementary only: never lose the bench line over it
             e2e["int32_indices"] = {"error": str(ex)[:200]}
@@ -479,16 +513,16 @@ def run_ours(args):
                       "bf16x3": "f32 (MLP products as 3 split-bf16 tcgen05 MMAs with f32 accumulate, inside the fp32 "
                                 "parity bound 1e-5*max|logit|; gather/FwFM in f32)"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: DeepFwFM dense (fwfm+deep+fwlw), F=39 (13 numeric), K=10, MLP "
-                                   "400x400x400, paper-Criteo cardinalities (1.33 M rows, 53 MB fp32), uniform indices",
+            "config": {"workload": WORKLOAD_TEXT,
                        "batch_per_gpu": B, "precision": args.precision,
-                       "l2": f"inputs cycle over {nb} distinct batches ({nb * B * 260 / 1e6:.0f} MB > 126 MB L2); "
-                             "the 53 MB of tables + 1.9 MB of weights stay L2-resident by design",
+                       "l2": f"inputs cycle over {nb} distinct batches ({nb * B * (CATS * 8 + NUM * 4) / 1e6:.0f} MB > 126 MB L2)" +
+                             ("; the 53 MB of tables + 1.9 MB of weights stay L2-resident by design" if args.workload == "criteo"
+                              else "; the tables are larger than L2 too"),
                        "launch": (f"CUDA graphs of {G} steps" if graphs else "stream launches") +
                                  (f", the independent forwards round-robin over {nstreams} concurrent streams" if nstreams > 1
                                   else ", strictly back to back on one stream"),
                        "tables": "one GPU" if world == 1 else
-                                 f"{len(model._shards)} of 26 categorical tables row-sharded over {world} GPUs (row i on rank i mod P); " + ("rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"
+                                 f"{len(model._shards)} of {CATS} categorical tables row-sharded over {world} GPUs (row i on rank i mod P); " + ("rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"
                                     if not pull else "rows fetched by direct peer loads over NVLink (no collective) by a pull kernel "
                                     "that runs ahead of the fused kernel into a local staging buffer (exchange='p2p_pull')")},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
@@ -504,7 +538,7 @@ def run_ours(args):
 def cpu_port_setup(B):
     from oracle import synth, torch_port
     from oracle.config import PathConfig
-    cfg = PathConfig(FIELD, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    cfg = PathConfig(FIELD, SIZES, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, **MODEL_KW)
     w = synth.make_weights(cfg, seed=42)
     sd = {k: torch.from_numpy(v) for k, v in w.items()}
     Xi, Xv = synth.make_inputs(cfg, B, seed=0)
@@ -558,8 +592,11 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+set_workload("criteo")       # the default for importers (scripts/*.py use make_model / make_batches)
+
 if __name__ == "__main__":
     a = parse()
+    set_workload(a.workload)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -1,6 +1,6 @@
 """Debug tool: per-CTA timeline of fused_forward_kernel (clock64 stamps), config 2, B=4096 by default.
 
-    python scripts/fused_timeline.py [B] [bf16|bf16x3]
+    python scripts/fused_timeline.py [B] [bf16|bf16x3] [criteo|criteo_qr|twitter]
 """
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,9 +12,10 @@ lib = _lib.load()
 dev = torch.device("cuda", 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
-m = bench.make_model(dev, prec, synth.CRITEO_PAPER)
+bench.set_workload(sys.argv[3] if len(sys.argv) > 3 else "criteo")
+m = bench.make_model(dev, prec, bench.SIZES)
 plan = m._get_plan(); plan.ensure_image(m, prec)
-Xi, Xv = bench.make_batches(dev, synth.CRITEO_PAPER, B, 4, seed=0)
+Xi, Xv = bench.make_batches(dev, bench.SIZES, B, 4, seed=0)
 out = torch.zeros(B, device=dev)
 nc = min((B + 31) // 32, 148)
 NCLK = 128
@@ -22,7 +23,7 @@ clk = torch.zeros(148 * NCLK, dtype=torch.int64, device=dev)
 fn = lib.dfw_debug_set_fused_clock_buffer; fn.argtypes = [ctypes.c_void_p]; fn.restype = None
 st = torch.cuda.current_stream().cuda_stream
 def run(j=0):
-    rc = lib.dfw_forward_fused(plan.model_ref, Xi[j].data_ptr(), 26, 1, Xv[j].data_ptr(), 13, 1, B, _lib.PRECISIONS[prec],
+    rc = lib.dfw_forward_fused(plan.model_ref, Xi[j].data_ptr(), bench.CATS, 1, Xv[j].data_ptr(), bench.NUM, 1, B, _lib.PRECISIONS[prec],
                                out.data_ptr(), None, None, st)
     _lib.check(rc, "dfw_forward_fused")
 for j in range(3): run(j)

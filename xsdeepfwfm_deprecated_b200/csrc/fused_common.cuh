@@ -76,7 +76,7 @@ __host__ __device__ inline int mtile_rows(int npad, int mt) {
 }
 
 // The symmetrised field matrix as a kernel parameter (same column layout as the shallow image's U).  valid = 0: absent.
-constexpr int MAX_U = 1152;                    // usize(47) + 4 = 1108 floats
+constexpr int MAX_U = 1168;                    // usize(47) + 4 = 1156 floats (usize(39) = 800)
 struct alignas(16) UParam { int valid; int pad_[3]; float u[MAX_U]; };
 
 struct RingPos {
