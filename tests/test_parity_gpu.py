@@ -561,3 +561,25 @@ def test_device_pruning_edge_cases():
     for k in before:
         changed = not torch.equal(before[k], after[k])
         assert changed == ("linear" in k and "weight" in k), k
+
+
+def test_device_pruning_reproduces_the_reference_pruned_fixture():
+    """tests/golden/pruned.npz was made by the REFERENCE: its own binary_search_threshold and masking on its own module, then
+    its forward.  Pruning the same unpruned weights on the device must give the same weights (checksum of every parameter),
+    the same non-zero census and, through the fused kernel, the reference's logits."""
+    import json
+    import os
+    from golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "pruned.npz"))
+    cfg = PathConfig.from_json(json.loads(str(z["cfg"])))
+    w = synth.make_weights(cfg, seed=int(z["seed"]), emb_scale=float(z["emb_scale"]))        # unpruned
+    assert synth.weights_checksum(w) != str(z["checksum"])
+    for precision, rel in (("fp32", FP32_REL), ("bf16x3", FP32_REL), ("fp32_csr", FP32_REL)):
+        m = to_cuda(cfg, w, precision=precision)
+        m.prune_one_shot(sparse=0.9, emb_r=0.444, emb_corr=1.0)
+        got_w = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        assert synth.weights_checksum(got_w) == str(z["checksum"]), precision
+        for k, n in json.loads(str(z["nnz"])).items():
+            assert int(np.count_nonzero(got_w[k])) == n, k
+        got = run(m, z["Xi"].astype(np.int64), z["Xv"].astype(np.float32))
+        assert np.abs(got - z["logits"]).max() <= logit_tol(z["logits"], rel), precision
