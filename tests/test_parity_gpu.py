@@ -583,3 +583,26 @@ def test_device_pruning_reproduces_the_reference_pruned_fixture():
             assert int(np.count_nonzero(got_w[k])) == n, k
         got = run(m, z["Xi"].astype(np.int64), z["Xv"].astype(np.float32))
         assert np.abs(got - z["logits"]).max() <= logit_tol(z["logits"], rel), precision
+
+
+def test_cached_loader_columns_feed_the_host_path(tmp_path):
+    """the binary cache of utils.data_preprocess (int32 indices, memory-mapped) goes through
+    predict_proba_host / eval_by_batch unchanged and gives the same bits as in-memory int64 arrays, for both index formats."""
+    from xsdeepfwfm_deprecated_b200.utils import data_preprocess as dp
+    t = load_tiny()
+    v = t["variants"]["deep_fwlw"]
+    w = tiny_weights(v)
+    n = 3000
+    Xi, Xv, y = t["Xi"][:n], t["Xv"][:n], t["y"][:n]
+    path = dp.write_cache(dict(index=Xi[:, :, 0], value=Xv, label=y.astype(np.int8), feature_sizes=v["cfg"].feature_sizes),
+                          str(tmp_path / "cache"))
+    c = dp.read_cache(path)
+    assert isinstance(c["index"], np.memmap) and c["index"].dtype == np.int32
+    for idt in ("int64", "int32"):
+        m = to_cuda(v["cfg"], w, precision="bf16x3", index_dtype=idt)
+        want = m.predict_proba_host(Xi, Xv, batch_size=1024)
+        got = m.predict_proba_host(c["index"], c["value"], batch_size=1024)
+        assert np.array_equal(got, want), idt
+        a = m.eval_by_batch(Xi, Xv, y, n)
+        b = m.eval_by_batch(c["index"], c["value"], c["label"], n)
+        assert a == b, idt

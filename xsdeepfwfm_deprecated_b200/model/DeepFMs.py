@@ -529,10 +529,11 @@ class DeepFMs(nn.Module):
         plan.ensure_image(self, self.precision)
         n = len(Xi_np)
         C_ = self.field_size - self.num
-        np_idx = np.int32 if self.index_dtype == "int32" else np.int64
         t_idx = torch.int32 if self.index_dtype == "int32" else torch.int64
-        Xi_np = np.ascontiguousarray(np.asarray(Xi_np, dtype=np_idx).reshape(n, C_))
-        Xv_np = np.ascontiguousarray(np.asarray(Xv_np, dtype=np.float32).reshape(n, -1)[:, :self.num])
+        # no whole-array conversion: memory-mapped columns (utils.data_preprocess.read_cache) are sliced per chunk and cast
+        # while they are copied into the pinned staging buffers
+        Xi_np = np.asarray(Xi_np).reshape(n, C_)
+        Xv_np = np.asarray(Xv_np).reshape(n, -1)
         bs = min(batch_size, max(n, 1))
         chunk = bs * max(1, min(batches_in_flight, -(-max(n, 1) // bs)))
         if plan.host_ws is None or plan.host_ws[0] != bs or plan.host_ws[1] != prec or plan.host_ws[2] < chunk:
@@ -550,9 +551,9 @@ class DeepFMs(nn.Module):
             for o in range(0, n, chunk):
                 e = min(n, o + chunk)
                 b = e - o
-                pxi.numpy()[:b * C_] = Xi_np[o:e].ravel()
+                pxi.numpy()[:b * C_].reshape(b, C_)[...] = Xi_np[o:e]
                 if self.num:
-                    pxv.numpy()[:b * self.num] = Xv_np[o:e].ravel()
+                    pxv.numpy()[:b * self.num].reshape(b, self.num)[...] = Xv_np[o:e, :self.num]
                 rc = lib.dfw_forward_host_stream(plan.model_ref, pxi.data_ptr(), pxv.data_ptr(), b, bs, prec,
                                                  ws.data_ptr(), ws.numel(), plogit.data_ptr() if want_logits else None,
                                                  pprob.data_ptr(), st)
