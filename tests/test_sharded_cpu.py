@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from xsdeepfwfm_deprecated_b200.sharded import exchange_rows, local_rows, owner_and_local, route_indices
+from xsdeepfwfm_deprecated_b200.sharded import exchange_rows, local_rows, owner_and_local, pull_plan, route_indices
 
 
 def test_partition_arithmetic():
@@ -32,6 +32,37 @@ def test_route_indices_is_a_stable_owner_sort():
     assert int(counts.sum()) == idx.numel()
     assert torch.equal(torch.sort(s % 4).values, s % 4)           # grouped by owner
     assert torch.equal(torch.bincount(idx % 4, minlength=4), counts)
+
+
+@pytest.mark.parametrize("world,c", [(2, 1), (4, 1), (8, 4), (3, 7)])
+def test_pull_plan_stages_the_rows_the_unsharded_lookup_reads(world, c):
+    """The p2p_pull exchange: pulling shard[owner][local] into staging row b and looking the rewritten index up in the
+    staging table (QR: quotient row * remainder row) reads exactly what the unsharded table gives for the original id."""
+    g = torch.Generator().manual_seed(world * 10 + c)
+    n, K, B = 1003, 10, 257
+    nq = -(-n // c)
+    Wq = torch.randn(nq, K, generator=g)
+    Wr = torch.randn(c, K, generator=g) if c > 1 else None
+    shards = [Wq[r::world].contiguous() for r in range(world)]                 # row i on rank i mod P at local row i div P
+    assert [s.shape[0] for s in shards] == [local_rows(nq, r, world) for r in range(world)]
+    idx = torch.randint(0, n, (B,), generator=g)
+    owner, local, rewritten = pull_plan(idx, c, world)
+    staged = torch.stack([shards[int(o)][int(l)] for o, l in zip(owner, local)])      # what dfw_pull_rows copies
+    assert torch.equal(staged, Wq[idx // c])
+    # the fused kernel's view: a (B * c)-category table whose quotient rows are `staged`
+    q2, r2 = rewritten // c, rewritten % c
+    assert torch.equal(q2, torch.arange(B)) and torch.equal(r2, idx % c) and int(rewritten.max()) < B * c
+    want = Wq[idx // c] * Wr[idx % c] if c > 1 else Wq[idx]
+    got = staged[q2] * Wr[r2] if c > 1 else staged[q2]
+    assert torch.equal(got, want)
+
+
+def test_exchange_names():
+    from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
+    with pytest.raises(ValueError):
+        ShardedDeepFMs(39, [1] * 13 + [10] * 26, exchange="smoke_signals", use_cuda=False)
+    for ex in ("p2p", "p2p_pull", "nccl"):
+        assert ShardedDeepFMs(39, [1] * 13 + [10] * 26, exchange=ex, use_cuda=False).exchange == ex
 
 
 def _free_port():

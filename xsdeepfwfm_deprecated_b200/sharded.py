@@ -58,6 +58,21 @@ def local_rows(rows: int, rank: int, world: int) -> int:
     return (rows - rank + world - 1) // world if rows > rank else 0
 
 
+def pull_plan(idx: torch.Tensor, collisions: int, world: int):
+    """What ``dfw_pull_rows`` does with one sharded column (pure torch restatement, used by the tests): for category ids
+    ``idx`` (B,) of a table with QR collision count ``collisions`` (1 = plain) it returns
+
+        owner, local   rank that stores the row and its position in that rank's shard (row = idx // c;  row mod P, row div P)
+        rewritten      the index the fused kernel gets instead: ``b * c + idx mod c`` -- row b of the (B * c)-category staging
+                       table whose quotient rows are the pulled rows, same remainder as the original id
+    """
+    c = max(int(collisions), 1)
+    row = torch.div(idx, c, rounding_mode="floor")
+    owner, local = owner_and_local(row, world)
+    b = torch.arange(idx.numel(), dtype=idx.dtype, device=idx.device)
+    return owner, local, b * c + (idx - row * c)
+
+
 def route_indices(idx: torch.Tensor, world: int):
     """Sort the requests of one rank by owner.  Returns (sorted global ids, send counts per owner, inverse permutation)."""
     owner = idx % world
