@@ -75,7 +75,7 @@ __host__ __device__ inline TileSizes tile_sizes(int F, int K, int num, int S) {
     t.bE = up16(sizeof(float) * S * t.EP);
     t.bPart = up16(sizeof(float) * K * S);
     t.bIdx = up16(sizeof(int32_t) * S * (C > 0 ? C : 1));
-    t.bXv = up16(sizeof(float) * S * (num > 0 ? num : 1));
+    t.bXv = up16(sizeof(float) * (S * (num > 0 ? num : 1) + num * K));     // dense values + one copy of the numeric rows
     return t;
 }
 
@@ -128,6 +128,7 @@ struct DivStep {
 struct GatherCtx {
     const dfw_field_desc* sF; const int32_t* sIdx; const float* sXv; float* sE;
     int F, K, num, C, EP, nrows, tid, nthreads;
+    float* sNum;     // (num, K): the single row of every numeric field, fetched once per tile (they follow the dense values)
 };
 
 // Adjacent lanes take adjacent 8-byte (SEGW = 2: all row bases 8-byte aligned, K even) or 4-byte pieces of the
@@ -136,18 +137,26 @@ struct GatherCtx {
 // PLAIN = no table of the model is QR or rank-sharded: branch-free body (row = w2 + idx * K).
 template <int SEGW, int FT, int KT, bool PLAIN>
 __device__ __forceinline__ void issue_rows(const GatherCtx& g) {
-    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
     const int K = KT > 0 ? KT : g.K;
     const uint32_t nV = (uint32_t)(K / SEGW);
-    const uint32_t total = (uint32_t)g.nrows * F * nV;
+    const uint32_t C = (uint32_t)g.C, num = (uint32_t)g.num;
+    // categorical fields: one row per (sample, field)
+    const uint32_t total = (uint32_t)g.nrows * C * nV;
 #pragma unroll 4
     for (uint32_t e = g.tid; e < total; e += g.nthreads) {
         const uint32_t row = e / nV, k = (e - row * nV) * SEGW;
-        const uint32_t s = row / F, f = row - s * F;
-        const int32_t idx = (int)f < g.num ? 0 : g.sIdx[s * g.C + (f - g.num)];
+        const uint32_t s = row / C, c = row - s * C, f = num + c;
+        const int32_t idx = g.sIdx[row];
         const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
         float* dst = g.sE + s * g.EP + f * K + k;
         if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
+    }
+    // numeric fields are one-row tables (model/DeepFMs.py:185-196): fetch each row ONCE per tile, not once per sample --
+    // they used to be a third of the gather's copies
+    for (uint32_t e = g.tid; e < num * nV; e += g.nthreads) {
+        const uint32_t f = e / nV, k = (e - f * nV) * SEGW;
+        const float* src = (PLAIN ? g.sF[f].w2 : locate_row(g.sF[f], 0, K)) + k;
+        if (SEGW == 2) cp_async8(g.sNum + f * K + k, src); else cp_async4(g.sNum + f * K + k, src);
     }
 }
 
@@ -155,31 +164,43 @@ __device__ __forceinline__ void issue_rows(const GatherCtx& g) {
 // (model/DeepFMs.py:334): one fp32 operation each, applied after the block's copies have landed.
 template <int FT, int KT>
 __device__ __forceinline__ void fixup_rows(const GatherCtx& g, bool any_qr) {
-    const uint32_t F = (uint32_t)(FT > 0 ? FT : g.F);
     const int K = KT > 0 ? KT : g.K;
-    const uint32_t total = (uint32_t)g.nrows * F;
+    // numeric fields: E[s, f, :] = row_f (x|+ remainder row 0 for a QR table) * Xv[s, f]
+    const uint32_t num = (uint32_t)g.num;
 #pragma unroll 1
-    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t s = e / F, f = e - s * F;
-        const bool numeric = (int)f < g.num;
-        if (!any_qr && !numeric) continue;
+    for (uint32_t e = g.tid; e < (uint32_t)g.nrows * num; e += g.nthreads) {
+        const uint32_t s = e / num, f = e - s * num;
         const dfw_field_desc& fd = g.sF[f];
         const int op = fd.qr_op;
-        if (op == DFW_TABLE_PLAIN && !numeric) continue;
+        const float x = g.sXv[e];
+        const float* row = g.sNum + f * K;
         float* dst = g.sE + s * g.EP + f * K;
-        const float x = numeric ? g.sXv[s * g.num + f] : 1.0f;
-        const float* rrow = nullptr;
-        if (op != DFW_TABLE_PLAIN) {
-            const int32_t idx = numeric ? 0 : g.sIdx[s * g.C + (f - g.num)];
-            const uint32_t c = (uint32_t)fd.collisions;
-            rrow = fd.w2_r + ((uint32_t)idx - ((uint32_t)idx / c) * c) * K;
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            float v = row[k];
+            if (op == DFW_TABLE_QR_MULT) v *= __ldg(fd.w2_r + k);
+            else if (op == DFW_TABLE_QR_ADD) v += __ldg(fd.w2_r + k);
+            dst[k] = v * x;
         }
+    }
+    if (!any_qr) return;
+    // categorical QR tables: quotient row (already in place) (x|+) remainder row
+    const uint32_t C = (uint32_t)g.C;
+#pragma unroll 1
+    for (uint32_t e = g.tid; e < (uint32_t)g.nrows * C; e += g.nthreads) {
+        const uint32_t s = e / C, c = e - s * C, f = num + c;
+        const dfw_field_desc& fd = g.sF[f];
+        const int op = fd.qr_op;
+        if (op == DFW_TABLE_PLAIN) continue;
+        float* dst = g.sE + s * g.EP + f * K;
+        const int32_t idx = g.sIdx[e];
+        const uint32_t cc = (uint32_t)fd.collisions;
+        const float* rrow = fd.w2_r + ((uint32_t)idx - ((uint32_t)idx / cc) * cc) * K;
 #pragma unroll 2
         for (int k = 0; k < K; ++k) {
             float v = dst[k];
             if (op == DFW_TABLE_QR_MULT) v *= __ldg(rrow + k);
-            else if (op == DFW_TABLE_QR_ADD) v += __ldg(rrow + k);
-            if (numeric) v *= x;
+            else v += __ldg(rrow + k);
             dst[k] = v;
         }
     }
@@ -298,7 +319,7 @@ __device__ __forceinline__ void embed_gather(const EmbedParams& p, const TileSme
     const bool vec2 = hdr->misaligned == 0 && (K % 2 == 0);    // all row bases 8-byte aligned
 
     // ------------------------------------------------------------------ phase B: gather
-    GatherCtx g{sF, sIdx, sXv, sE, F, K, num, C, EP, nrows, tid, nthreads};
+    GatherCtx g{sF, sIdx, sXv, sE, F, K, num, C, EP, nrows, tid, nthreads, sXv + S * (num > 0 ? num : 1)};
     if (!any_qr) { if (vec2) issue_rows<2, FT, KT, true>(g); else issue_rows<1, FT, KT, true>(g); }
     else         { if (vec2) issue_rows<2, FT, KT, false>(g); else issue_rows<1, FT, KT, false>(g); }
     // rows of samples past the end of the batch: zeros (never written out, keeps phase D finite)
