@@ -334,7 +334,9 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         float* prob_d = static_cast<float*>(mapped_alias(prob_host));
         const bool direct = host_transport_override() == 3;
         const size_t stage_bytes = H.oLogit;            // the Xi + Xv part of a slot
-        DFW_REQUIRE(direct || (size_t)kStage * stage_bytes <= workspace_bytes, DFW_E_WORKSPACE, "workspace too small for the staging slots");
+        // as many staging slots as the workspace holds (it is sized for the staged transport's 3 full slots: at least 3 fit)
+        const int nstage = (int)(workspace_bytes / stage_bytes < (size_t)kStage ? workspace_bytes / stage_bytes : (size_t)kStage);
+        DFW_REQUIRE(direct || nstage >= 2, DFW_E_WORKSPACE, "workspace too small for two staging slots");
         if (!direct) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->start, 0));
         int64_t done = 0;
         for (int64_t i = 0; done < N; ++i, done += batch) {
@@ -344,10 +346,10 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
             const char* xv_src = xv_d ? xv_d + (size_t)done * num * sizeof(float) : nullptr;
             const void* xi_in = xi_src;
             const void* xv_in = xv_src;
-            const int slot = (int)(i % kStage);
+            const int slot = (int)(i % (direct ? kStage : nstage));
             if (!direct) {
                 char* ws = static_cast<char*>(workspace) + (size_t)slot * stage_bytes;
-                if (i >= kStage) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->freed[slot], 0));   // the slot's previous batch has been consumed
+                if (i >= nstage) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->freed[slot], 0));   // the slot's previous batch has been consumed
                 static const int pull_ctas = getenv("DFW_PULL_CTAS") ? atoi(getenv("DFW_PULL_CTAS")) : 64;   // 64 x 128 threads x 32 B in flight
                 stage_inputs_kernel<<<pull_ctas, 128, 0, hp->pull>>>(xi_src, ws + H.oXi, C > 0 ? (size_t)b * C * ib : 0,
                                                               xv_src, ws + H.oXv, num > 0 ? (size_t)b * num * sizeof(float) : 0);

@@ -483,10 +483,16 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HB) = __float2bfloat16_rn(0.f);
         }
         if (owner) {
+            // element (k = f * KT + kk, sample smp): chunk (k / 64) * CH + (smp / 8) * X_SBO + (k % 64) * 16 + (smp % 8) * 2.  With f
+            // unrolled everything but "does f * KT + kk cross into the next 64-wide chunk" is a compile-time constant.
+            unsigned char* const xbase = sX + (smp >> 3) * X_SBO + (smp & 7) * 2 + kk * 16;
+            constexpr int JUMP = CH - 64 * 16;
 #pragma unroll
             for (int f = 0; f < FT; ++f) {
-                const int col = f * KT + kk;
-                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (smp >> 3) * X_SBO + (col & 63) * 16 + (smp & 7) * 2;
+                const int c0 = f * KT, lo = c0 & 63;
+                int off = c0 * 16 + (c0 >> 6) * JUMP;
+                if (lo + KT > 64) off += (kk >= 64 - lo) ? JUMP : 0;
+                unsigned char* dst = xbase + off;
                 const __nv_bfloat16 hi = __float2bfloat16_rn(e[f]);
                 *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
                 if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HB) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
