@@ -141,15 +141,34 @@ __device__ __forceinline__ void issue_rows(const GatherCtx& g) {
     const uint32_t nV = (uint32_t)(K / SEGW);
     const uint32_t C = (uint32_t)g.C, num = (uint32_t)g.num;
     // categorical fields: one row per (sample, field)
-    const uint32_t total = (uint32_t)g.nrows * C * nV;
+    if (C == 0) {
+        // no categorical field at all
+    } else if ((uint32_t)g.nthreads % nV == 0) {
+        // the group is a whole number of rows wide: a thread keeps its piece and walks rows tid / nV, + nthreads / nV, ...
+        // with (sample, column) advanced incrementally -- no division in the loop
+        const uint32_t row0 = (uint32_t)g.tid / nV, k = ((uint32_t)g.tid - row0 * nV) * SEGW, rstep = (uint32_t)g.nthreads / nV;
+        const uint32_t nrow = (uint32_t)g.nrows * C;
+        DivStep st(row0, rstep, C);
 #pragma unroll 4
-    for (uint32_t e = g.tid; e < total; e += g.nthreads) {
-        const uint32_t row = e / nV, k = (e - row * nV) * SEGW;
-        const uint32_t s = row / C, c = row - s * C, f = num + c;
-        const int32_t idx = g.sIdx[row];
-        const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
-        float* dst = g.sE + s * g.EP + f * K + k;
-        if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
+        for (uint32_t row = row0; row < nrow; row += rstep) {
+            const uint32_t s = st.q, f = num + st.r;
+            const int32_t idx = g.sIdx[row];
+            const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
+            float* dst = g.sE + s * g.EP + f * K + k;
+            if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
+            st.next();
+        }
+    } else {
+        const uint32_t total = (uint32_t)g.nrows * C * nV;
+#pragma unroll 4
+        for (uint32_t e = g.tid; e < total; e += g.nthreads) {
+            const uint32_t row = e / nV, k = (e - row * nV) * SEGW;
+            const uint32_t s = row / C, c = row - s * C, f = num + c;
+            const int32_t idx = g.sIdx[row];
+            const float* src = (PLAIN ? g.sF[f].w2 + (int64_t)idx * K : locate_row(g.sF[f], idx, K)) + k;
+            float* dst = g.sE + s * g.EP + f * K + k;
+            if (SEGW == 2) cp_async8(dst, src); else cp_async4(dst, src);
+        }
     }
     // numeric fields are one-row tables (model/DeepFMs.py:185-196): fetch each row ONCE per tile, not once per sample --
     // they used to be a third of the gather's copies
