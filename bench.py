@@ -11,8 +11,12 @@ MLP 400x400x400, paper-Criteo cardinalities, B = 4096 per GPU).  Prints ONE JSON
   e2e       samples/s through the host-buffer C-ABI call dfw_forward_host: pinned host batches -> H2D -> kernels
             -> sigmoid -> D2H -> sync, every step inside the timed region
   roofline  the dominant kernel stage, timed live with CUDA events (algorithmic bytes / flops per SURVEY 8(d))
-  cpu_baseline / --impl reference: oracle/torch_port.py (the reference's op sequence, fp32 torch CPU) on the
-            host cores -- the reference is a Python module and does not travel to the GPU box; kind "port"
+  parity    before anything is timed, the timed call path's logits for this rank's batch 0 against oracle/closed_form.py
+            on the model's real weights (every --gpus N, every --workload)
+  cpu_baseline / --impl reference: the UNMODIFIED reference module from baseline/_ref (a git-ignored copy of
+            /root/reference/{model,utils} made by __graft_entry__.build(); kind "reference"), fp32 torch CPU on the host
+            cores; oracle/torch_port.py (kind "port") only when that copy is absent
+  reference_cuda  supplementary: the same unmodified module with use_cuda=True on this GPU (eager PyTorch)
 """
 import argparse
 import json
@@ -33,18 +37,26 @@ METRIC = "DeepFwFM inference samples/sec"
 UNIT = "samples/s"
 K_EMB, NODES, DEPTH = 10, 400, 3
 FIELD = NUM = CATS = 0
-SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT = None, {}, "", False
+SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT, PRUNED = None, {}, "", False, False
 ALG_BYTES_PER_SAMPLE = ALG_BYTES_PER_BATCH = MLP_FLOPS_PER_SAMPLE = 0
 
 
 def set_workload(name):
     """criteo = BASELINE config 2 (the headline); criteo_qr = config 4(ii); twitter = config 5's shape (supplementary lines)."""
     global FIELD, NUM, CATS, SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT, ALG_BYTES_PER_SAMPLE, ALG_BYTES_PER_BATCH, MLP_FLOPS_PER_SAMPLE
-    from oracle import synth
+    from xsdeepfwfm_deprecated_b200.utils import workloads as synth
+    global PRUNED
+    PRUNED = False
+    XV_UNIT = False
     if name == "criteo":
         FIELD, NUM, SIZES, MODEL_KW = 39, 13, synth.CRITEO_PAPER, {}
         WORKLOAD_TEXT = ("BASELINE config 2: DeepFwFM dense (fwfm+deep+fwlw), F=39 (13 numeric), K=10, MLP 400x400x400, "
                          "paper-Criteo cardinalities (1.33 M rows, 53 MB fp32), uniform indices")
+    elif name == "criteo_pruned":
+        FIELD, NUM, SIZES, MODEL_KW, PRUNED = 39, 13, synth.CRITEO_PAPER, {}, True
+        WORKLOAD_TEXT = ("BASELINE config 3: config 2's model after the reference's one-shot pruning recipe (DeepFMs.prune_one_shot: "
+                         "sparse 0.9 on the MLP layers, fwfm_linear and |R|; 0.9*0.444 over the stacked embeddings), zeros kept inside "
+                         "the dense tensors as the reference saves them; uniform indices")
     elif name == "criteo_qr":
         FIELD, NUM, SIZES = 39, 13, synth.CRITEO_KAGGLE
         MODEL_KW = dict(embedding_bag=1, qr_flag=1, qr_operation="mult", qr_collisions=4, qr_threshold=200)
@@ -72,7 +84,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--workload", default="criteo", choices=["criteo", "criteo_qr", "twitter"],
+    ap.add_argument("--workload", default="criteo", choices=["criteo", "criteo_pruned", "criteo_qr", "twitter"],
                     help="criteo = BASELINE config 2 (the headline line); the others are supplementary shapes")
     ap.add_argument("--precision", default=os.environ.get("DFW_BENCH_PRECISION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32", "fp32_csr"])
@@ -134,7 +146,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- workload
-def make_model(device, precision, feature_sizes, world=1, exchange=None, index_dtype="int64"):
+def make_model(device, precision, feature_sizes, world=1, exchange=None, index_dtype="int64", keep_weights=None):
     # exchange: "p2p" = peer loads inside the fused kernel (one launch per step; the default: measured 35.0 us/step at 2 GPUs);
     # "p2p_pull" = the same loads by a separate pull kernel ahead of the fused kernel (two launches; measured 36.7 us/step: the
     # pull CTAs overlap the fused kernels only partly)
@@ -154,9 +166,39 @@ def make_model(device, precision, feature_sizes, world=1, exchange=None, index_d
         for n_, p_ in m.named_parameters():
             if "fm_2nd_embeddings" in n_ and not n_.endswith("weight_r"):
                 p_.mul_(10.0)                              # trained-scale embeddings
+    if PRUNED:              # config 3: the reference's one-shot recipe (model/DeepFMs.py:647-673) at the paper's rates, on the device
+        m.eval()
+        m.prune_one_shot(sparse=0.9, emb_r=0.444, emb_corr=1.0)
+    if keep_weights is not None:        # fp32 parameters as the oracle takes them -- captured BEFORE the tables are sharded
+        keep_weights.update({k: v.detach().cpu().numpy() for k, v in m.state_dict().items()})
     if world > 1:
         m.shard_()          # every rank built identical full tables (same seed); keep only this rank's rows
     return m.eval().freeze()
+
+
+PARITY_BOUND = {"fp32": 1e-5, "bf16x3": 1e-5, "fp32_csr": 1e-5, "bf16": 5e-4}
+
+
+def oracle_parity(weights, Xi0, Xv0, got, precision, n=256):
+    """Every timed arm checks itself first: the logits the timed call path produced for the first `n` samples of this rank's
+    batch 0 against the fp64 closed form (oracle/closed_form.py, pinned to the reference by tests/golden) evaluated on the
+    model's real fp32 parameters (for sharded tables: captured before shard_()).  The oracle is the checker here, nothing else."""
+    from oracle import closed_form
+    from oracle.config import PathConfig
+    cfg = PathConfig(FIELD, SIZES, embedding_size=K_EMB, numerical=NUM, use_fm=False, use_fwfm=True, use_deep=True,
+                     use_fwlw=True, h_depth=DEPTH, deep_nodes=NODES, **MODEL_KW)
+    n = min(n, Xi0.shape[0])
+    ref = closed_form.forward(cfg, weights, Xi0[:n].cpu().numpy(), Xv0[:n].cpu().numpy())
+    g = got[:n].double().cpu().numpy()
+    scale = float(np.abs(ref["logit"]).max())
+    rel = float(np.abs(g - ref["logit"]).max() / scale)
+    shallow = ref["first"] + ref["second"] + float(weights["bias"][0])
+    deep_rel = float(np.abs((g - shallow) - ref["deep"]).max() / max(float(np.abs(ref["deep"]).max()), 1e-30))
+    bound = PARITY_BOUND[precision]
+    out = dict(max_rel=rel, bound=bound, n=int(n), vs="oracle/closed_form (fp64)", max_abs_logit=round(scale, 4),
+               deep_term_rel=deep_rel, ok=bool(rel <= bound))
+    assert rel <= bound, f"parity: max|dlogit|/max|logit| = {rel:.3e} > {bound:g} on the timed path"
+    return out
 
 
 def make_batches(device, feature_sizes, B, nb, seed):
@@ -198,7 +240,8 @@ def run_ours(args):
     lib = _lib.load()
     sizes = SIZES
     B, nb = args.batch, args.nbatches
-    model = make_model(device, args.precision, sizes, world)
+    weights = {}
+    model = make_model(device, args.precision, sizes, world, keep_weights=weights)
     Xi, Xv = make_batches(device, sizes, B, nb, seed=rank)
     plan = model._get_plan()
     plan.ensure_image(model, args.precision)
@@ -276,9 +319,23 @@ def run_ours(args):
     step(0)
     launches_per_step = lib.dfw_launch_count() - l0
     torch.cuda.synchronize(device)
+    # parity of the timed call path (this rank's batch 0 as step() just computed it) against the oracle, before anything is timed
+    parity = oracle_parity(weights, Xi[0], Xv[0], logits[0], args.precision)
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref_cuda = reference_cuda(device, B, weights, Xi[0], Xv[0])
+        if "logits" in ref_cuda:        # the reference's own fp32 GPU forward against ours on the same batch
+            r_ = ref_cuda.pop("logits").float()
+            ref_cuda["max_rel_vs_ours"] = float((r_ - logits[0]).abs().max() / r_.abs().max())
+        torch.cuda.empty_cache()
+    del weights
+    if dist:        # every rank checks its own batch; the line reports the worst
+        t = torch.tensor([parity["max_rel"], parity["deep_term_rel"]], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity.update(max_rel=float(t[0].item()), deep_term_rel=float(t[1].item()), ranks=world)
 
     # K steps as CUDA-graph replays of G-step segments (each segment walks distinct batches)
-    graphs, G = [], 0
+    graphs, tails, G = [], {}, 0
     if args.graph:
         G = min(16, args.steps)
         nseg = max(1, min(nb // G, 16))
@@ -287,6 +344,18 @@ def run_ours(args):
             with torch.cuda.graph(g, stream=stream):
                 steps_on_lanes(s * G, G)
             graphs.append(g)
+
+    def tail_graph(r):       # the k mod G steps left over run from a graph of their own: no eager launches in the timed region
+        if r not in tails:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                steps_on_lanes((nb - r) % nb, r)
+            tails[r] = g
+        return tails[r]
+
+    if graphs:
+        for k_ in {max(args.warmup, 3) % G, args.steps % G} - {0}:
+            tail_graph(k_)
 
     def run_steps(k):
         if not graphs:
@@ -300,7 +369,7 @@ def run_ours(args):
                 done += G
                 s += 1
             if k - done:
-                steps_on_lanes(0, k - done)
+                tail_graph(k - done).replay()
 
     run_steps(max(args.warmup, 3))
     barrier()
@@ -335,7 +404,7 @@ def run_ours(args):
 
     pk = peaks()
     n_it = 64
-    fused = bool(lib.dfw_fused_supported(plan.model_ref, prec)) and not os.environ.get("DFW_NO_FUSED")
+    fused = bool(lib.dfw_fused_supported(plan.model_ref, prec))
     step_bytes = ALG_BYTES_PER_SAMPLE * B + ALG_BYTES_PER_BATCH
     if fused:
         # one kernel per step: gather + FwFM (HBM/L2 side) and the MLP (tensor side) overlap inside it
@@ -526,7 +595,7 @@ def run_ours(args):
                                     if not pull else "rows fetched by direct peer loads over NVLink (no collective) by a pull kernel "
                                     "that runs ahead of the fused kernel into a local staging buffer (exchange='p2p_pull')")},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
         }
         print(json.dumps(out))
     if dist:
@@ -535,32 +604,111 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------- CPU arms
-def cpu_port_setup(B):
-    from oracle import synth, torch_port
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")        # git-ignored copy of /root/reference/{model,utils} made by build()
+
+
+def _oracle_cfg():
     from oracle.config import PathConfig
-    cfg = PathConfig(FIELD, SIZES, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, **MODEL_KW)
+    return PathConfig(FIELD, SIZES, embedding_size=K_EMB, numerical=NUM, use_fm=False, use_fwfm=True, use_deep=True,
+                      use_fwlw=True, h_depth=DEPTH, deep_nodes=NODES, **MODEL_KW)
+
+
+def reference_module(cfg, sd, cuda=False):
+    """The UNMODIFIED reference class (model/DeepFMs.py:47) from baseline/_ref with the given state_dict, in eval mode;
+    None when the copy is absent (then the arms fall back to oracle/torch_port.py and say kind = 'port')."""
+    if not os.path.exists(os.path.join(REF_DIR, "model", "DeepFMs.py")):
+        return None
+    import logging
+    import warnings
+    warnings.filterwarnings("ignore")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    from model.DeepFMs import DeepFMs as RefDeepFMs          # the reference itself
+    log = logging.getLogger("reference")
+    log.addHandler(logging.NullHandler())
+    log.propagate = False
+    m = RefDeepFMs(cfg.field_size, cfg.feature_sizes, embedding_size=cfg.embedding_size, h_depth=cfg.h_depth,
+                   deep_nodes=cfg.deep_nodes, use_fm=cfg.use_fm, use_fwfm=cfg.use_fwfm, use_deep=cfg.use_deep,
+                   use_fwlw=cfg.use_fwlw, use_lw=cfg.use_lw, use_cuda=bool(cuda), numerical=cfg.numerical,
+                   embedding_bag=cfg.embedding_bag, qr_flag=cfg.qr_flag, qr_operation=cfg.qr_operation,
+                   qr_collisions=cfg.qr_collisions, qr_threshold=cfg.qr_threshold, logger=log)
+    m.load_state_dict(sd, strict=True)
+    if cuda:            # model/DeepFMs.py:961-963
+        m.use_cuda = True
+        m = m.cuda()
+    return m.eval()
+
+
+def cpu_arm_setup(B):
+    """(forward callable, kind, description) of the CPU arm on config 2's weights and one B-sample batch."""
+    from oracle import synth, torch_port
+    cfg = _oracle_cfg()
     w = synth.make_weights(cfg, seed=42)
+    if PRUNED:
+        from oracle import prune
+        w = prune.one_shot_prune(w, 0.9, 0.444, 1.0)
     sd = {k: torch.from_numpy(v) for k, v in w.items()}
-    Xi, Xv = synth.make_inputs(cfg, B, seed=0)
-    return cfg, sd, torch.from_numpy(Xi), torch.from_numpy(Xv), torch_port
+    Xi, Xv = synth.make_inputs(cfg, B, seed=0, xv="unit" if XV_UNIT else "int50")
+    Xi, Xv = torch.from_numpy(Xi), torch.from_numpy(Xv)
+    ref = reference_module(cfg, sd, cuda=False)
+    port = lambda: torch_port.forward(cfg, sd, Xi, Xv)        # noqa: E731
+    if ref is None:
+        return port, "port", "oracle/torch_port.py (the reference's op sequence restated; baseline/_ref is absent)"
+
+    def fwd():
+        with torch.no_grad():
+            return ref(Xi, Xv)
+
+    # the reference and its restatement agree on this very batch (fp32 rounding only) -- keeps the port honest too
+    a, b = fwd(), port()
+    assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()), "baseline/_ref and oracle/torch_port disagree"
+    return fwd, "reference", ("the unmodified reference module (baseline/_ref/model/DeepFMs.py, DeepFMs.forward in eval mode under "
+                              "torch.no_grad, use_cuda=False)")
 
 
 def cpu_port_baseline(B, budget_s):
-    cfg, sd, Xi, Xv, torch_port = cpu_port_setup(B)
+    fwd, kind, what = cpu_arm_setup(B)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch_port.forward(cfg, sd, Xi, Xv)
+    fwd()
     times = []
     t_start = time.perf_counter()
     while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 50):
         t0 = time.perf_counter()
-        torch_port.forward(cfg, sd, Xi, Xv)
+        fwd()
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return dict(value=round(B / statistics.median(times), 1), unit=UNIT, cores=cores, kind="port",
+    return dict(value=round(B / statistics.median(times), 1), unit=UNIT, cores=cores, kind=kind,
                 best=round(B / best, 1),
-                sample=f"{len(times)} forwards of the same B={B} config-2 batch through oracle/torch_port.py "
-                       f"(reference op sequence, fp32, torch {torch.__version__} CPU, {cores} threads), median")
+                sample=f"{len(times)} forwards of the same B={B} batch through {what}, fp32, torch {torch.__version__} CPU, "
+                       f"{cores} threads, median")
+
+
+def reference_cuda(device, B, weights, Xi0, Xv0, iters=20):
+    """Supplementary yardstick (SURVEY 8(d) 'optional extra'): the unmodified reference module with use_cuda=True on this same
+    B200 (eager aten kernels + cuBLAS SGEMM, model/DeepFMs.py:1012-1022), same weights, same batch, CUDA events around forward."""
+    cfg = _oracle_cfg()
+    try:
+        ref = reference_module(cfg, {k: torch.from_numpy(v) for k, v in weights.items()}, cuda=True)
+        if ref is None:
+            return {"unavailable": "baseline/_ref is absent"}
+        with torch.no_grad():
+            out = ref(Xi0, Xv0)
+            for _ in range(3):
+                ref(Xi0, Xv0)
+            torch.cuda.synchronize(device)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                ref(Xi0, Xv0)
+            b.record()
+            b.synchronize()
+        ms = a.elapsed_time(b) / iters
+        return dict(value=round(B / (ms * 1e-3), 1), unit=UNIT, ms_per_step=round(ms, 4), iters=iters,
+                    what="unmodified reference DeepFMs.forward, use_cuda=True, eager PyTorch on this GPU, fp32 "
+                         f"(TF32 off), device-resident inputs, B={B}", logits=out)
+    except Exception as ex:
+        return {"unavailable": str(ex)[:200]}
 
 
 def run_reference(args):
@@ -568,26 +716,23 @@ def run_reference(args):
     if rank != 0:
         return
     B = args.batch
-    cfg, sd, Xi, Xv, torch_port = cpu_port_setup(B)
+    fwd, kind, what = cpu_arm_setup(B)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     steps = min(args.steps, 60)          # bounded: each step is one full B=4096 forward on the CPU (~0.1-0.4 s)
     for _ in range(min(max(args.warmup, 1), 3)):
-        torch_port.forward(cfg, sd, Xi, Xv)
+        fwd()
     t0 = time.perf_counter()
     for _ in range(steps):
-        torch_port.forward(cfg, sd, Xi, Xv)
+        fwd()
     dt = time.perf_counter() - t0
     v = round(B * steps / dt, 1)
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": min(max(args.warmup, 1), 3), "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "BASELINE config 2 (same as the GPU arm), one B=4096 batch per step on the host CPU",
-                      "batch_per_gpu": B},
-           "cpu_baseline": dict(value=v, unit=UNIT, cores=cores, kind="port",
-                                sample=f"{steps} forwards of B={B} through oracle/torch_port.py (the reference's op "
-                                       f"sequence, fp32 torch CPU, {cores} threads); the reference itself is a Python "
-                                       "module under /root/reference and does not travel to the GPU box"),
+           "config": {"workload": WORKLOAD_TEXT + f" -- one B={B} batch per step on the host CPU", "batch_per_gpu": B},
+           "cpu_baseline": dict(value=v, unit=UNIT, cores=cores, kind=kind,
+                                sample=f"{steps} forwards of B={B} through {what}, fp32 torch CPU, {cores} threads"),
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 

@@ -32,15 +32,16 @@ def _rows(cfg: PathConfig, params: Dict[str, np.ndarray], prefix: str, f: int,
     """
     if cfg.is_qr(f):
         c = cfg.qr_collisions
-        wq = params[f"{prefix}.{f}.weight_q"].astype(dtype)
-        wr = params[f"{prefix}.{f}.weight_r"].astype(dtype)
         q, r = idx // c, idx % c
+        # rows first, cast after (same values; a 16.7 M-row table is not converted to look up a few hundred rows)
+        wq = params[f"{prefix}.{f}.weight_q"][q].astype(dtype)
+        wr = params[f"{prefix}.{f}.weight_r"][r].astype(dtype)
         if cfg.qr_operation == "mult":
-            return wq[q] * wr[r]
+            return wq * wr
         if cfg.qr_operation == "add":
-            return wq[q] + wr[r]
+            return wq + wr
         raise ValueError("qr_operation 'concat' changes the embedding width; not on the hot path")
-    return params[f"{prefix}.{f}.weight"].astype(dtype)[idx]
+    return params[f"{prefix}.{f}.weight"][idx].astype(dtype)
 
 
 def gather_block(cfg: PathConfig, params, Xi: np.ndarray, Xv: np.ndarray,

@@ -24,4 +24,4 @@ for _ in range(3): run()
 t0 = time.perf_counter()
 for _ in range(10): run()
 t = (time.perf_counter() - t0) / (10 * nh)
-print(f"{prec} DFW_E2E_SKIP={os.environ.get('DFW_E2E_SKIP', '0')}: {t * 1e6:.1f} us/step -> {B / t / 1e6:.1f} M samples/s")
+print(f"{prec}: {t * 1e6:.1f} us/step -> {B / t / 1e6:.1f} M samples/s")

@@ -26,13 +26,16 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for tag, kw, precision in (("plain", {}, "fp32"), ("qr", dict(qr_flag=1, qr_collisions=4, qr_threshold=200), "fp32"),
-                               ("plain", {}, "bf16x3"), ("qr", dict(qr_flag=1, qr_collisions=4, qr_threshold=200), "bf16x3")):
-        cfg = PathConfig(39, SIZES, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, deep_nodes=64, **kw)
+    QR = dict(qr_flag=1, qr_collisions=4, qr_threshold=200)
+    # fwlw = False: first order from the fm_1st_embeddings tables (plain and QR), indexed by the original category ids
+    for tag, kw, precision, fwlw in (("plain", {}, "fp32", True), ("qr", QR, "fp32", True), ("plain", {}, "bf16x3", True),
+                                     ("qr", QR, "bf16x3", True), ("plain1", {}, "bf16x3", False), ("qr1", QR, "bf16x3", False),
+                                     ("qr1", QR, "fp32", False)):
+        cfg = PathConfig(39, SIZES, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=fwlw, deep_nodes=64, **kw)
         w = synth.make_weights(cfg, seed=5)
         Xi, Xv = synth.make_inputs(cfg, 777 + 13 * rank, seed=50 + rank)          # ragged, different per rank
         tXi, tXv = torch.from_numpy(Xi).to(dev), torch.from_numpy(Xv).to(dev)
-        common = dict(use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True, deep_nodes=64, use_cuda=True,
+        common = dict(use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=fwlw, deep_nodes=64, use_cuda=True,
                       precision=precision, **kw)
         base = DeepFMs(39, SIZES, **common)
         base.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
@@ -41,7 +44,7 @@ def main():
             want = base(tXi, tXv)
         ref = closed_form.forward(cfg, w, Xi, Xv)["logit"]
         assert np.abs(want.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
-        for exchange in ("p2p", "p2p_pull", "nccl"):
+        for exchange in (("p2p", "p2p_pull", "nccl") if fwlw else ("p2p",)):
             m = ShardedDeepFMs(39, SIZES, exchange=exchange, shard_threshold=200, **common)
             m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
             m = m.to(dev).eval()

@@ -72,3 +72,17 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_shipped_library_reads_no_experiment_switch_from_the_environment(lib):
+    """a benchmarked .so must not hold an environment variable that removes or reroutes timed work.  The
+    knobs exist only in a -DDFW_DEBUG build; the default build has none of their names in it, and the work-skipping ones
+    (DFW_E2E_SKIP, DFW_DEBUG_SKIP_INTERACTION) are gone from the sources altogether."""
+    from xsdeepfwfm_deprecated_b200 import _lib
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for name in (b"DFW_E2E_SKIP", b"DFW_DEBUG_SKIP_INTERACTION", b"DFW_NO_FUSED", b"DFW_HOST_TRANSPORT", b"DFW_FUSED_PAIR",
+                 b"DFW_FUSED_CLUSTER", b"DFW_FUSED_STAGES", b"DFW_PULL_CTAS", b"DFW_PULL_ROWS_CTAS"):
+        assert name not in blob, name
+    src = "".join(open(p).read() for p in glob.glob(os.path.join(ROOT, "xsdeepfwfm_deprecated_b200", "csrc", "*")))
+    assert "DFW_E2E_SKIP" not in src and "SKIP_INTERACTION" not in src
+    assert not re.search(r"(?<!dbg_)getenv\(", src.replace("return getenv(name)", ""))

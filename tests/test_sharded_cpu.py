@@ -62,7 +62,7 @@ def test_exchange_names():
     with pytest.raises(ValueError):
         ShardedDeepFMs(39, [1] * 13 + [10] * 26, exchange="smoke_signals", use_cuda=False)
     for ex in ("p2p", "p2p_pull", "nccl"):
-        assert ShardedDeepFMs(39, [1] * 13 + [10] * 26, exchange=ex, use_cuda=False).exchange == ex
+        assert ShardedDeepFMs(39, [1] * 13 + [10] * 26, exchange=ex, use_cuda=False, use_fwlw=True).exchange == ex
 
 
 def _free_port():
@@ -109,3 +109,17 @@ def test_all_to_all_row_exchange_gloo(world):
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) == "ok" for r in range(world))
+
+
+def test_index_rewriting_exchanges_refuse_first_order_tables():
+    """'nccl' / 'p2p_pull' rewrite the sharded index columns, which the first-order tables (use_fwlw=0) are
+    looked up with -- refused at construction; 'p2p' keeps the category ids and is allowed."""
+    import pytest
+    from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
+    sizes = [1] * 13 + [50] * 26
+    kw = dict(use_fm=False, use_fwfm=True, use_deep=True, use_cuda=False, deep_nodes=16)
+    for ex in ("nccl", "p2p_pull"):
+        with pytest.raises(ValueError, match="use_fwlw"):
+            ShardedDeepFMs(39, sizes, exchange=ex, use_fwlw=False, **kw)
+        ShardedDeepFMs(39, sizes, exchange=ex, use_fwlw=True, **kw)
+    ShardedDeepFMs(39, sizes, exchange="p2p", use_fwlw=False, **kw)

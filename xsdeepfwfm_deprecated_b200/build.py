@@ -1,6 +1,6 @@
 """Build libdeepfwfm_sm100a.so in-tree with nvcc (sm_100a only).
 
-    python -m xsdeepfwfm_deprecated_b200.build [--force] [--verbose]
+    python -m xsdeepfwfm_deprecated_b200.build [--force] [--verbose] [--debug]
 
 The .so stays inside the package directory so it travels with the repo snapshot to the GPU box;
 it is git-ignored.  nvcc cross-compiles without a GPU.
@@ -44,17 +44,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """debug=True adds -DDFW_DEBUG: the experiment knobs (DFW_FUSED_*, DFW_HOST_TRANSPORT, DFW_NO_FUSED, DFW_PULL_*) are then read
+    from the environment.  The default (shipped / benchmarked) build reads no environment variable."""
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp")
-    dig = _digest()
+    dig = _digest() + ("+debug" if debug else "")
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DDFW_DEBUG"] if debug else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
@@ -75,4 +78,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug="--debug" in sys.argv))

@@ -153,7 +153,7 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
         m = &local;
     }
     // one kernel for the whole forward when the tensor-core form fits the model's shapes
-    static const bool no_fused = getenv("DFW_NO_FUSED") != nullptr;
+    static const bool no_fused = dbg_getenv("DFW_NO_FUSED") != nullptr;
     if (deep && !no_fused && (precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3) && dfw_fused_supported(m, precision))
         return dfw_forward_fused(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, precision, logits_out,
                                  prob_out, err_word, stream);
@@ -277,7 +277,7 @@ void* mapped_alias(const void* host) {
 // 3 = mapped without the pull stage (debug: the fused kernel's gather warps read Xi / Xv from host memory themselves)
 int host_transport_override() {
     static const int v = [] {
-        const char* e = getenv("DFW_HOST_TRANSPORT");
+        const char* e = dbg_getenv("DFW_HOST_TRANSPORT");
         if (!e) return 0;
         return !strcmp(e, "copy") ? 1 : !strcmp(e, "mapped") ? 2 : !strcmp(e, "mapped_direct") ? 3 : 0;
     }();
@@ -288,7 +288,7 @@ int host_transport_override() {
 extern "C" int dfw_host_transport_is_mapped(const dfw_model* m, int precision, const void* xi_host, const void* xv_host,
                                             const void* logits_host, const void* prob_host) {
     if (!m || check_model(m)) return 0;
-    if (host_transport_override() == 1 || getenv("DFW_NO_FUSED")) return 0;
+    if (host_transport_override() == 1 || dbg_getenv("DFW_NO_FUSED")) return 0;
     const int C = m->field_size - m->numerical, num = m->numerical;
     if (!(m->flags & DFW_USE_DEEP) || !(precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3) ||
         !dfw_fused_supported(m, precision))
@@ -350,7 +350,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
             if (!direct) {
                 char* ws = static_cast<char*>(workspace) + (size_t)slot * stage_bytes;
                 if (i >= nstage) DFW_CUDA_OK(cudaStreamWaitEvent(hp->pull, hp->freed[slot], 0));   // the slot's previous batch has been consumed
-                static const int pull_ctas = getenv("DFW_PULL_CTAS") ? atoi(getenv("DFW_PULL_CTAS")) : 64;   // 64 x 128 threads x 32 B in flight
+                static const int pull_ctas = dbg_getenv("DFW_PULL_CTAS") ? atoi(dbg_getenv("DFW_PULL_CTAS")) : 64;   // 64 x 128 threads x 32 B in flight
                 stage_inputs_kernel<<<pull_ctas, 128, 0, hp->pull>>>(xi_src, ws + H.oXi, C > 0 ? (size_t)b * C * ib : 0,
                                                               xv_src, ws + H.oXv, num > 0 ? (size_t)b * num * sizeof(float) : 0);
                 count_launch();
@@ -374,8 +374,7 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         return 0;
     }
     DFW_REQUIRE(host_transport_override() < 2, DFW_E_UNSUPPORTED,
-                "DFW_HOST_TRANSPORT=mapped, but a host buffer is not pinned or the fused kernel does not take this model");
-    static const int dbg_skip = getenv("DFW_E2E_SKIP") ? atoi(getenv("DFW_E2E_SKIP")) : 0;   // debug: 1 = no H2D, 2 = no kernels
+                "the mapped host transport was forced (debug build), but a host buffer is not pinned or the fused kernel does not take this model");
     int64_t done = 0;
     for (int64_t i = 0; done < N; ++i, done += batch) {
         const int64_t b = N - done < batch ? N - done : batch;
@@ -386,14 +385,13 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         float* xv = reinterpret_cast<float*>(ws + H.oXv);
         float* logit = reinterpret_cast<float*>(ws + H.oLogit);
         float* prob = reinterpret_cast<float*>(ws + H.oProb);
-        if (C > 0 && dbg_skip != 1 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xi, reinterpret_cast<const char*>(xi_host) + (size_t)done * C * ib, (size_t)b * C * ib, cudaMemcpyHostToDevice, st));
-        if (num > 0 && dbg_skip != 1 && dbg_skip != 3 && dbg_skip != 4) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (dbg_skip < 2)
+        if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi, reinterpret_cast<const char*>(xi_host) + (size_t)done * C * ib, (size_t)b * C * ib, cudaMemcpyHostToDevice, st));
+        if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv, xv_host + done * num, (size_t)b * num * sizeof(float), cudaMemcpyHostToDevice, st));
         if (int rc = dfw_forward(m, xi, C, 1, xv, num, 1, b, precision, ws + H.oFwd, slot_bytes - H.oFwd,
                                  logits_host ? logit : nullptr, prob_host ? prob : nullptr, nullptr, st))
             return rc;
         if (logits_host) DFW_CUDA_OK(cudaMemcpyAsync(logits_host + done, logit, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (prob_host && dbg_skip != 3) DFW_CUDA_OK(cudaMemcpyAsync(prob_host + done, prob, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (prob_host) DFW_CUDA_OK(cudaMemcpyAsync(prob_host + done, prob, (size_t)b * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kSlots; ++i) {
         DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "deepfwfm_b200.h"
@@ -69,5 +70,14 @@ inline int check_model(const dfw_model* m) {
 __device__ __forceinline__ float sigmoidf_dev(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tuning / experiment knobs are read from the environment ONLY in a -DDFW_DEBUG build (python -m ...build --debug).  The
+// shipped library reads no environment variable at all, so nothing outside the caller's arguments can change what a timed
+// call does.
+#ifdef DFW_DEBUG
+inline const char* dbg_getenv(const char* name) { return getenv(name); }
+#else
+inline const char* dbg_getenv(const char*) { return nullptr; }
+#endif
 
 }  // namespace dfw

@@ -52,7 +52,6 @@ struct Params {
     int* err;
     long long* clk;                             // optional per-CTA timeline (debug tooling): FZ_NCLK x int64 per CTA
     volatile int* prog;                         // optional progress markers in pinned host memory (debug): 32 ints per CTA
-    int dbg_skip_interaction;                   // debug (timeline experiments only): leave the dense second order out -- WRONG logits
 };
 #define FZ_PROG(slot, val) do { if (p.prog && lane == 0) p.prog[blockIdx.x * 32 + (slot)] = (val); } while (0)
 #define FZ_NCLK 128

@@ -515,7 +515,7 @@ fused_pair_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 }
                 acc = a0 + a1;
             }
-            if (!use_list && !p.dbg_skip_interaction) {
+            if (!use_list) {
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int j = 1; j < FT; ++j) {

@@ -746,11 +746,11 @@ static int get_maps(const dfw_model* m, bool split, int cluster, int in_dim, Map
 }
 
 static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
+    const char* e = dbg_getenv(name);
     return e ? atoi(e) : dflt;
 }
 static int env_cluster() {
-    static const int v = [] { const char* e = getenv("DFW_FUSED_CLUSTER"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = dbg_getenv("DFW_FUSED_CLUSTER"); return e ? atoi(e) : 0; }();
     return v;
 }
 
@@ -870,10 +870,6 @@ extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t 
     p.fc = m->fc; p.logits = logits_out; p.prob = prob_out; p.B = B;
     p.num_tiles = (int)((B + fz::TS - 1) / fz::TS);
     p.err = err_word; p.clk = fz::g_clk; p.prog = fz::g_prog;
-    {   // debug switch for scripts/fused_timeline.py: only honoured while a timeline buffer is installed
-        static const bool skip = getenv("DFW_DEBUG_SKIP_INTERACTION") != nullptr;
-        p.dbg_skip_interaction = (skip && fz::g_clk) ? 1 : 0;
-    }
     // U = strict upper triangle of (R + R^T) / 2 by columns, in fp32 exactly as pack_shallow_kernel computes it
     pl.up.valid = 0;
     if ((m->flags & DFW_USE_FWFM) && m->field_cov_host && usize(F) + 4 <= fz::MAX_U) {

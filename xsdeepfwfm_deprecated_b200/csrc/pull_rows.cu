@@ -136,7 +136,7 @@ extern "C" int dfw_pull_rows(const dfw_model* m, const int32_t* sharded_fields, 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static const int cap = getenv("DFW_PULL_ROWS_CTAS") ? atoi(getenv("DFW_PULL_ROWS_CTAS")) : 0;
+    static const int cap = dbg_getenv("DFW_PULL_ROWS_CTAS") ? atoi(dbg_getenv("DFW_PULL_ROWS_CTAS")) : 0;
     if (cap > 0) sms = cap;
     const int grid = (int)(chunks > sms ? sms : chunks);
     const size_t smem = (size_t)ROWS * p.K * sizeof(float);

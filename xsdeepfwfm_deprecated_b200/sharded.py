@@ -12,21 +12,22 @@ and a 1/P slice of every large table):
 
 Three exchange modes produce bit-identical logits (rows are copied, never summed):
 
-``p2p`` (one launch, lowest latency)
+``p2p`` (one launch; the default, and what ``bench.py --gpus N`` runs)
     Every rank's shard is cudaMalloc'ed by ``dfw_shard_alloc`` and exported with CUDA IPC; each rank maps all peers'
     shards and puts the P pointers into the field descriptors.  The SAME fused gather kernel then fetches a row with
     one ``cp.async`` from whichever GPU owns it -- over NVLink 5 / NVSwitch when it is a peer -- straight into the
     sample's shared-memory block.  Gather, exchange and the FwFM interaction are one kernel: no index exchange, no
     staging buffers, no collective on the data path.
 
-``p2p_pull`` (highest throughput: what ``bench.py --gpus N`` runs)
+``p2p_pull`` (an option; measured slower than ``p2p`` at 2 GPUs; needs ``use_fwlw=1``)
     The same peer loads, issued by a separate small kernel (``dfw_pull_rows``) one batch AHEAD of the fused kernel: its
     128-thread CTAs fit beside a resident fused CTA, copy every sharded field's row of every sample from the owning GPU
     into a batch-ordered staging buffer in local HBM and rewrite the index columns; the fused kernel then gathers from
     local memory at single-GPU speed instead of holding an SM idle through NVLink round trips.  One ``PullLane``
     (staging + descriptors) per concurrent stream.
 
-``nccl`` (the baseline the p2p kernels are measured against)
+``nccl`` (the baseline the p2p kernels are measured against; needs ``use_fwlw=1``; it reads the split sizes back to the
+    host and synchronises the stream every forward, so its number is a baseline, not a tuned collective path)
     The textbook exchange: route indices to their owners with ``all_to_all_single``, owners gather the requested rows
     (``dfw_gather_rows``), a second ``all_to_all_single`` returns them, and the fused kernel consumes them as a
     per-batch table.
@@ -114,6 +115,12 @@ class ShardedDeepFMs(DeepFMs):
         super().__init__(*args, **kw)
         if exchange not in ("p2p", "p2p_pull", "nccl"):
             raise ValueError("exchange must be 'p2p', 'p2p_pull' or 'nccl'")
+        if exchange != "p2p" and not self.use_fwlw:
+            # 'nccl' and 'p2p_pull' rewrite the sharded index columns to positions in a per-batch staging table
+            # (b * c + idx mod c); the first-order tables (use_fwlw=0: fm_1st_embeddings[f][idx], model/DeepFMs.py:300-309) are
+            # looked up with the same column and would read row b instead of the category's row.  'p2p' keeps the ids.
+            raise ValueError(f"exchange={exchange!r} needs use_fwlw=1 (the first-order tables are indexed by the original "
+                             "category ids, which this exchange rewrites); use exchange='p2p'")
         self.process_group = process_group
         self.shard_threshold = shard_threshold
         self.exchange = exchange
