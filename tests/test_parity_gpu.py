@@ -14,7 +14,8 @@ from test_module_cpu import build
 
 pytestmark = pytest.mark.gpu
 FP32_REL = 1e-5
-BF16_REL = 5e-4
+BF16_REL = 5e-4           # bf16 path, logit-relative: holds wherever the shallow (fp32) term sets the logit scale (configs 1-4)
+BF16_DEEP_REL = 1.2e-2    # bf16 path in general: the whole error is the MLP's operand rounding, <= 1.2e-2 * max|deep| (measured <= 9.1e-3)
 
 
 def to_cuda(cfg, weights, **kw):
@@ -75,7 +76,8 @@ def test_golden_logits_bf16(name):
         return
     got = run(m, c["Xi"], c["Xv"])
     # the shallow part stays fp32; only the deep term carries bf16 operand rounding
-    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], BF16_REL) + 2e-2 * np.abs(
+    # the shallow part stays fp32: all of the error is the MLP's bf16 operand rounding, bounded against the deep term's own scale
+    assert np.abs(got - c["logits"]).max() <= logit_tol(c["logits"], FP32_REL) + BF16_DEEP_REL * np.abs(
         closed_form.forward(c["cfg"], c["weights"], c["Xi"], c["Xv"])["deep"]).max()
 
 
@@ -273,7 +275,7 @@ def test_bf16_ragged_and_multi_tile(B):
     got = run(to_cuda(cfg, c["weights"], precision="bf16"), Xi, Xv)
     ref = closed_form.forward(cfg, c["weights"], Xi, Xv)
     assert got.shape == (B,)
-    assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], BF16_REL) + 2e-2 * np.abs(ref["deep"]).max()
+    assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], FP32_REL) + BF16_DEEP_REL * np.abs(ref["deep"]).max()
 
 
 def test_bf16_equals_fp32_on_bf16_representable_problem():
@@ -330,7 +332,7 @@ def test_bf16x3_ragged_and_multi_tile(B):
     cfg = c["cfg"]
     Xi, Xv = synth.make_inputs(cfg, B, seed=B)
     ref = closed_form.forward(cfg, c["weights"], Xi, Xv)
-    for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", BF16_REL, 2e-2 * np.abs(ref["deep"]).max())):
+    for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", FP32_REL, BF16_DEEP_REL * np.abs(ref["deep"]).max())):
         got = run(to_cuda(cfg, c["weights"], precision=precision), Xi, Xv)
         assert got.shape == (B,)
         err = np.abs(got - ref["logit"]).max()
@@ -398,7 +400,7 @@ def test_fused_kernels_odd_widths_and_depths(nodes, depth):
     for B in (20, 333):
         Xi, Xv = synth.make_inputs(cfg, B, seed=B + nodes)
         ref = closed_form.forward(cfg, w, Xi, Xv)
-        for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", BF16_REL, 2e-2 * np.abs(ref["deep"]).max())):
+        for precision, rel, extra in (("bf16x3", FP32_REL, 0.0), ("bf16", FP32_REL, BF16_DEEP_REL * np.abs(ref["deep"]).max())):
             if nodes > 512 and precision == "bf16":
                 continue            # bf16 has no staged form for widths > 512 (documented limit); bf16x3 falls back to fp32
             got = run(to_cuda(cfg, w, precision=precision), Xi, Xv)
