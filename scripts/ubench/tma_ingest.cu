@@ -67,7 +67,8 @@ int main() {
     const int SM = 12 * 16384 + 2048;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
     const int boxes = 21 * 20;
-    for (int cl : {1, 4}) for (int box_rows : {64, 128, 256}) for (int nstage : {6}) for (int grid : {128}) {
+    for (int cl : {1}) for (int box_rows : {128, 256}) for (int nstage : {2, 3, 4, 5, 6, 8, 12}) for (int grid : {64, 148}) {
+        if ((size_t)nstage * box_rows * 128 > 12 * 16384) continue;
         CUtensorMap map;
         if (make_map(&map, W, rows, cols, cols, box_rows / cl)) return 1;
         cudaLaunchConfig_t cfg = {};

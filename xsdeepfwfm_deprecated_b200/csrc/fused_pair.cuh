@@ -70,6 +70,7 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
 // wait with cluster-scope acquire (the producers of these barriers may be threads of the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* err, int code) {
     const uint32_t addr = smem_u32(bar);
+    unsigned long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
         asm volatile(
@@ -78,7 +79,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
-        if (spin > (1u << 28)) {     // ~10 s: only a broken pipeline gets here (profilers and debuggers stretch waits a lot)
+        if ((spin & 0x3ffu) == 0x3ffu && watchdog_expired(t0)) {     // only a broken pipeline gets here
             if (err) atomicExch(err, code);
             __trap();
         }

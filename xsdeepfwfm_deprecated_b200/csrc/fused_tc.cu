@@ -39,6 +39,7 @@
 //   Limits of the fused form: depth <= 4, widths <= 512, F*K <= 512, K <= 20.  Other shapes take the staged path.
 #include "fused_common.cuh"
 #include "fused_pair.cuh"
+#include "fused_wide.cuh"
 
 namespace dfw {
 namespace fz {
@@ -780,10 +781,85 @@ static int launch_pair(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st
     return check_launch("fused_pair_kernel");
 }
 
+// Persistent 64-sample pair kernel (fused_wide.cuh).  Shared-memory plan: X (64 samples) | weight ring | shallow image | per-column
+// partial sums | numeric rows | barriers.  Returns false when it does not fit (the caller then takes the 32-sample kernels).
+static int env_wide() {
+    static const int v = env_int("DFW_FUSED_WIDE", 1);
+    return v;
+}
+static bool make_plan_wide(const dfw_model* m, bool split, const Plan& pl, wd::WideParams& wp, size_t& smem_bytes) {
+    const int F = m->field_size, K = m->embedding_size, num = m->numerical;
+    wp.p = pl.p;
+    Params& p = wp.p;
+    const int CH = (split ? 2 : 1) * (int)wd::X_HBW;
+    size_t o = ((size_t)p.x_chunks * CH + 1023) / 1024 * 1024;
+    p.oE = 0;
+    p.oRing = (uint32_t)o;
+    const size_t img = up16(img_layout(F, K).total), part = up16(sizeof(float) * K * wd::TSW), nrow = up16(sizeof(float) * (num > 0 ? num : 1) * K);
+    const size_t tail = img + part + nrow + up16(sizeof(wd::WideBars)) + 64;
+    if (o + tail + 1024 + 2 * (size_t)STAGE_BYTES > SMEM_LIMIT) return false;
+    int ns = (int)((SMEM_LIMIT - 1024 - o - tail) / STAGE_BYTES);
+    if (ns > wd::NS_MAX) ns = wd::NS_MAX;
+    {
+        static const int cap = env_int("DFW_FUSED_STAGES", 0);
+        if (cap >= 2 && cap < ns) ns = cap;
+    }
+    if (ns < (split ? 4 : 2)) return false;
+    wp.ns = ns;
+    o += (size_t)ns * STAGE_BYTES; p.oImg = (uint32_t)o;
+    o += img;                       p.oPart = (uint32_t)o;
+    o += part;                      wp.oNum = (uint32_t)o;
+    o += nrow;                      p.oMisc = (uint32_t)((o + 15) & ~size_t(15));
+    p.oIdx = p.oXv = 0;
+    smem_bytes = p.oMisc + sizeof(wd::WideBars) + 1024;
+    return smem_bytes <= SMEM_LIMIT;
+}
+
+template <bool SPLIT, int FT, int KT, int NUMT>
+static int launch_wide(const dfw_model* m, const Plan& pl, Maps& maps, cudaStream_t st, bool& taken) {
+    taken = false;
+    if (!pl.up.valid || m->numerical != NUMT) return 0;       // needs the field matrix as a kernel parameter
+    wd::WideParams wp;
+    size_t smem_bytes = 0;
+    if (!make_plan_wide(m, SPLIT, pl, wp, smem_bytes)) return 0;
+    taken = true;
+    wp.p.cluster = 2;
+    if (int rc = get_maps(m, SPLIT, 1, wp.p.in_dim, maps)) return rc;    // whole 128-row boxes: each CTA loads its own tile
+    auto kern = wd::fused_wide_kernel<SPLIT, FT, KT, NUMT>;
+    static thread_local bool configured_dev[16] = {};       // per device: function attributes are per context
+    static thread_local int sm_count[16] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& configured = configured_dev[cur_dev & 15];
+    if (!configured) {
+        DFW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur_dev);
+        sm_count[cur_dev & 15] = sms;
+        configured = true;
+    }
+    const long long tiles = (wp.p.B + wd::TSW - 1) / wd::TSW;
+    wp.n_pair_tiles = (int)((tiles + 1) / 2);
+    int pairs = sm_count[cur_dev & 15] / 2;
+    {
+        static const int cap = env_int("DFW_FUSED_PAIRS", 0);
+        if (cap > 0 && cap < pairs) pairs = cap;
+    }
+    if (wp.n_pair_tiles < pairs) pairs = wp.n_pair_tiles;
+    kern<<<(unsigned)(2 * pairs), wd::THREADS, smem_bytes, st>>>(maps, pl.up, wp);
+    count_launch();
+    return check_launch("fused_wide_kernel");
+}
+
 template <bool SPLIT, int FT, int KT>
 static int run(const dfw_model* m, Plan& pl, Maps& maps, cudaStream_t st) {
     Params& p = pl.p;
     if constexpr (FT > 0) {
+        if (env_wide()) {      // every batch size: one kernel per model keeps a sample's bits independent of the batch it arrives in
+            bool taken = false;
+            const int rc = launch_wide<SPLIT, FT, KT, (FT == 39 ? 13 : 11)>(m, pl, maps, st, taken);
+            if (taken) return rc;
+        }
         if (env_pair() && p.num_tiles >= 2) return launch_pair<SPLIT, FT, KT>(m, pl, maps, st);
     }
     // cluster size: the largest of {4, 2, 1} that still covers all tiles in the fewest waves
@@ -878,6 +954,11 @@ extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t 
             for (int i = 0; i < pad4(j); ++i)
                 pl.up.u[ucol_off(j) + i] = i < j ? (cov[j * F + i] + cov[i * F + j]) * 0.5f : 0.f;
         pl.up.valid = 1;
+    } else if (!(m->flags & DFW_USE_FWFM) && usize(F) + 4 <= fz::MAX_U) {
+        // FM (model/DeepFMs.py:353-355): every pair weighs 1; valid = 2 marks "ones" for the kernels that walk the pair list otherwise
+        for (int j = 1; j < F; ++j)
+            for (int i = 0; i < pad4(j); ++i) pl.up.u[ucol_off(j) + i] = i < j ? 1.f : 0.f;
+        pl.up.valid = 2;
     }
     fz::Maps maps;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -1,0 +1,654 @@
+// The fused forward as a PERSISTENT, software-pipelined CTA pair with 64 samples per CTA (round 2; replaces the one-wave
+// 32-sample pair kernel of fused_pair.cuh as the default for the dataset shapes).
+//
+// What changed against fused_pair.cuh and why (measured there: 49 k cycles per 32-sample tile, of which 12 k were the gather in
+// front of the first MMA, 3 x 3 k the hand-offs between layers, and every N = 64 MMA ran at 40 cycles against a 32-cycle floor
+// because a 128-row weight operand costs 4 KB of shared-memory reads per instruction whatever N is):
+//   * 64 samples per CTA, 128 per pair: every MMA is M = 256 x N = 128 x K = 16 -- the weight bytes streamed from L2 and read
+//     from shared memory are the same as for N = 64, so the instruction sits on the 64-cycle math floor and every fixed latency
+//     is paid once per 128 samples.  TMEM: 2 (layer parity) x 2 (pair-tiles) x 128 columns = all 512.
+//   * persistent: a pair walks pair-tiles q = cluster, cluster + n_clusters, ...; the gather group runs one tile AHEAD of the
+//     tensor pipe.  There is no fp32 staging block any more (X for 64 samples + the weight ring leave no room for one): a gather
+//     thread owns (sample, embedding column), loads its column of every field's row straight into registers (ten lanes cover
+//     one 40-byte row, three rows per warp instruction -- whole sectors, no cp.async pieces, no fix-up pass), holds the first
+//     32 samples' values while the previous tile's last layer still reads X, and writes the bf16 (hi | lo) operand the moment
+//     the tensor pipe releases X (x_free = tcgen05.commit after the tile's last MMA).  First order + FwFM second order then run
+//     from the registers under layer 1's MMAs, as before.
+//   * one MMA issuer, one weight ring, and a HYBRID order inside a layer: [pair-tile 0: chunks 0-3][pair-tile 1: chunks 0-3]
+//     [pair-tile 0: chunks 4..][pair-tile 1: chunks 4..].  Pair-tile 0 (neurons 0..255 = the next layer's chunks 0-3) completes a
+//     quarter of a layer early, its epilogue runs under pair-tile 1's last MMAs, and the next layer starts on chunks 0-3 while
+//     the epilogue of pair-tile 1 (chunks 4..) is still running.  X stays ONE buffer: chunks 0-3 are dead after segment 2,
+//     chunks 4.. after the layer's last MMA.
+//   * the dense field matrix is always the kernel-parameter (constant-bank) form; a pruned R runs through it with its zeros
+//     (the pair-list walk needed the fp32 block).
+//
+//   warps 0      TMA producer (both CTAs): its own 128-row half of every (pair-tile, chunk[, hi|lo]) box, ring of NS slots,
+//                signals the LEADER's full[slot] (cp.async.bulk.tensor ... cta_group::2), which expects both halves
+//   warp  1      MMA issuer (leader only): tcgen05.mma.cta_group::2, commits multicast to both CTAs
+//   warps 2-3    idle (keep warp % 4 == TMEM lane quarter for the epilogue warps)
+//   warps 4-11   epilogue: set h = (warp - 4) / 4 takes sample columns [64 h, 64 h + 64) of each pair-tile = the samples of CTA h;
+//                thread = neuron (TMEM lane).  + bias, ReLU, split to bf16 hi/lo, 16-byte stores into CTA h's X
+//                (st.shared::cluster to the peer); last layer: x net_1_fc, warp transpose-reduction into CTA h's `red`
+//   warps 12-23  gather group: 3 samples x 10 columns per warp, two rounds of 32 samples per tile
+#pragma once
+#include "fused_pair.cuh"
+
+namespace dfw {
+namespace fz {
+namespace wd {
+
+constexpr int TSW = 64;                        // samples per CTA and tile
+constexpr int W_MMA = 1, N_PROD = 3;          // producers: warps 0, 2, 3
+constexpr int W_EPI0 = 4, W_EPI = 8;
+constexpr int W_G0 = W_EPI0 + W_EPI, W_G = 12;
+constexpr int THREADS = 32 * (W_G0 + W_G);     // 768: 80 registers per thread
+constexpr int CORE_THREADS = 32 * W_G0;
+constexpr int G_THREADS_W = 32 * W_G;
+constexpr int NS_MAX = 6;
+constexpr int BAR_G = 1, BAR_SETUP = 3, BAR_COREW = 4;
+constexpr uint32_t X_HBW = 8 * X_SBO;          // hi (or lo) part of one 64-wide K chunk: 64 samples
+
+struct WideBars {
+    uint64_t full[NS_MAX];           // leader: both CTAs' boxes of the slot have landed
+    uint64_t empty[NS_MAX];          // per CTA: slot consumed (multicast commit)
+    uint64_t x_ready;                // leader: layer-1 operand of the tile written in both CTAs (2 x W_G arrives)
+    uint64_t x_free;                 // per CTA: every MMA of the tile has completed, X may be overwritten (multicast commit)
+    uint64_t x_free03;               // per CTA: chunks 0-3 of X are dead already (after segment 2 of the tile's last layer)
+    uint64_t shallow_ready;          // per CTA: W_G arrives per tile
+    uint64_t act_ready[2][MAX_MT];   // leader: [layer parity][neuron tile], W_EPI arrives from the CTA that owns the tile
+    uint64_t acc_full[2][2];         // per CTA: [layer parity][pair-tile] accumulators complete (multicast commit)
+    uint64_t fin;                    // per CTA: the partial sums of its samples are in `red` (2 x 4 arrives per tile)
+    uint32_t tmem_holder, pad_;
+    float shallow[2][TSW];           // [tile parity]
+    float red[2][2][4][TSW];         // [tile parity][source CTA][lane quarter][sample]
+};
+
+struct WideParams {
+    Params p;
+    int n_pair_tiles;                // ceil(ceil(B / 64) / 2)
+    int ns;                          // ring slots
+    uint32_t oNum;                   // (num, K) floats: the single row of every numeric field, fetched once per CTA
+};
+
+// step i of a layer's MMA sequence -> (pair-tile, chunk); see the header: [0: 0..sp)[1: 0..sp)[0: sp..kch)[1: sp..kch)
+__device__ __forceinline__ void wide_step(int i, int PT, int kch, int& pt, int& c) {
+    const int sp = kch < 4 ? kch : 4;
+    if (PT == 1) { pt = 0; c = i; }
+    else if (i < sp) { pt = 0; c = i; }
+    else if (i < 2 * sp) { pt = 1; c = i - sp; }
+    else {
+        const int j = i - 2 * sp, rem = kch - sp;
+        if (j < rem) { pt = 0; c = sp + j; } else { pt = 1; c = sp + j - rem; }
+    }
+}
+// after which step pair-tile 0's accumulators may be handed to the epilogue: they are complete AND no MMA of the layer reads
+// chunks 0-3 (which that epilogue overwrites) any more
+__device__ __forceinline__ int wide_pt0_done(int PT, int kch) {
+    const int sp = kch < 4 ? kch : 4;
+    if (PT == 1) return kch - 1;
+    return kch > sp ? 2 * sp + (kch - sp) - 1 : 2 * sp - 1;
+}
+
+// one round of the gather: this thread's column `kk` of every field of global sample b  (model/DeepFMs.py:312-337,
+// model/QREmbeddingBag.py:156-174).  Exactly the reference's arithmetic: a row copy; one fp32 (*|+) for a QR table; one fp32
+// multiply by Xv for a numeric field.
+// low 32 bits of one index: every table has < 2^31 rows, so the low word decides (a negative int64 has a low word >= rows or,
+// for -2^32 k + small, is caught by the high-word pass below when DFW_CHECK_INDEX is on)
+__device__ __forceinline__ uint32_t load_index_lo(const EmbedParams& p, int64_t elem) {
+    if (p.flags & DFW_XI_INT32) return (uint32_t)__ldg(reinterpret_cast<const int32_t*>(p.xi) + elem);
+    return (uint32_t)__ldg(reinterpret_cast<const int32_t*>(p.xi) + 2 * elem);          // little endian
+}
+
+template <int FT, int KT, int NUMT, bool PLAIN>
+__device__ __forceinline__ void wide_load(const EmbedParams& ep, const dfw_field_desc* sF, const float* sNum, int64_t b,
+                                          bool live, int kk, float (&e)[FT]) {
+    constexpr int CT = FT - NUMT;
+    if (live) {
+        uint32_t idx[CT > 0 ? CT : 1];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) idx[c] = load_index_lo(ep, b * ep.xi_sb + c * ep.xi_sc);
+        if (ep.err) {       // DFW_CHECK_INDEX: the full 64-bit value must be inside the table
+#pragma unroll 1
+            for (int c = 0; c < CT; ++c) {
+                const int64_t v = load_index(ep, b * ep.xi_sb + c * ep.xi_sc);
+                if (v < 0 || v >= sF[NUMT + c].rows) atomicExch(ep.err, 1 + NUMT + c);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const dfw_field_desc& fd = sF[NUMT + c];
+            if (idx[c] >= (uint32_t)fd.rows) idx[c] = 0;          // defined behaviour instead of a wild read
+            const float* src = PLAIN ? fd.w2 + (size_t)idx[c] * KT : locate_row(fd, (int32_t)idx[c], KT);
+            e[NUMT + c] = __ldg(src + kk);
+        }
+        if constexpr (!PLAIN) {
+            // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172); the c-row remainder tables are L1-resident
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const dfw_field_desc& fd = sF[NUMT + c];
+                const int op = fd.qr_op;
+                if (op != DFW_TABLE_PLAIN) {
+                    const uint32_t cc = (uint32_t)fd.collisions;
+                    const float r = __ldg(fd.w2_r + (idx[c] - (idx[c] / cc) * cc) * KT + kk);
+                    e[NUMT + c] = op == DFW_TABLE_QR_MULT ? e[NUMT + c] * r : e[NUMT + c] + r;
+                }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NUMT; ++f) {
+            float v = sNum[f * KT + kk];
+            if constexpr (!PLAIN) {
+                const int op = sF[f].qr_op;
+                if (op == DFW_TABLE_QR_MULT) v *= __ldg(sF[f].w2_r + kk);
+                else if (op == DFW_TABLE_QR_ADD) v += __ldg(sF[f].w2_r + kk);
+            }
+            e[f] = v * ep.xv[b * ep.xv_sb + f * ep.xv_sc];
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < FT; ++f) e[f] = 0.f;
+    }
+}
+
+// first-order table terms of this thread's fields f = kk, kk + K, ... (use_fwlw = 0; model/DeepFMs.py:300-309, 445-450)
+template <int FT, int KT, int NUMT>
+__device__ __forceinline__ float wide_first(const EmbedParams& ep, const dfw_field_desc* sF, int64_t b, bool live, int kk) {
+    float acc = 0.f;
+    if (!live) return acc;
+#pragma unroll 4
+    for (int f = kk; f < FT; f += KT) {
+        const dfw_field_desc& fd = sF[f];
+        int64_t iv = 0;
+        if (f >= NUMT) {
+            iv = load_index(ep, b * ep.xi_sb + (f - NUMT) * ep.xi_sc);
+            if (iv < 0 || iv >= fd.rows) iv = 0;
+        }
+        const int32_t idx = (int32_t)iv;
+        float v;
+        if (fd.qr1_op != DFW_TABLE_PLAIN) {
+            const uint32_t c = (uint32_t)fd.collisions;
+            const uint32_t q = (uint32_t)idx / c, rr = (uint32_t)idx - q * c;
+            const float a = __ldg(fd.w1 + q), bq = __ldg(fd.w1_r + rr);
+            v = fd.qr1_op == DFW_TABLE_QR_MULT ? a * bq : a + bq;
+        } else {
+            v = __ldg(fd.w1 + idx);
+        }
+        if (f < NUMT) v *= ep.xv[b * ep.xv_sb + f * ep.xv_sc];
+        if (ep.flags & DFW_USE_LW) v *= __ldg(ep.fm1 + f);
+        acc += v;
+    }
+    return acc;
+}
+
+// bf16 (hi | lo) operand columns of fields [F0, F1) of tile-local sample s:  element (k = f * KT + kk, s) lives at
+// (k / 64) * CH + (s / 8) * X_SBO + (k % 64) * 16 + (s % 8) * 2  (+ X_HBW for the lo part).  With f unrolled everything but "does
+// f * KT + kk cross into the next 64-wide chunk" is a compile-time constant.
+template <bool SPLIT, int FT, int KT, int F0, int F1>
+__device__ __forceinline__ void wide_write(unsigned char* sX, int s, int kk, const float (&e)[FT]) {
+    constexpr int CH = (SPLIT ? 2 : 1) * (int)X_HBW, JUMP = CH - 64 * 16;
+    unsigned char* const xbase = sX + (s >> 3) * X_SBO + (s & 7) * 2 + kk * 16;
+#pragma unroll
+    for (int f = F0; f < F1; ++f) {
+        const int c0 = f * KT, lo = c0 & 63;
+        int off = c0 * 16 + (c0 >> 6) * JUMP;
+        if (lo + KT > 64) off += (kk >= 64 - lo) ? JUMP : 0;
+        unsigned char* dst = xbase + off;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(e[f]);
+        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+        if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
+    }
+}
+
+// first order (fwlw: <E_f, fwfm_linear_f>, model/DeepFMs.py:338-347) + FwFM / FM second order (model/DeepFMs.py:351-367) of one
+// (sample, column) from registers; every U_ij is a constant-bank operand of its FFMA, four independent chains per column j
+template <int FT, int KT>
+__device__ __forceinline__ float wide_interact(const float (&e)[FT], const UParam& up, const float* sWl, int kk, bool fwlw, float first) {
+    float acc = first;
+    if (fwlw) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int f = 0; f < FT; ++f) {
+            if (f & 1) a1 = fmaf(e[f], sWl[f * KT + kk], a1); else a0 = fmaf(e[f], sWl[f * KT + kk], a0);
+        }
+        acc = a0 + a1;
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 1; j < FT; ++j) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const float u = up.u[ucol_off(j) + i];
+            if ((i & 3) == 0) d0 = fmaf(u, e[i], d0);
+            else if ((i & 3) == 1) d1 = fmaf(u, e[i], d1);
+            else if ((i & 3) == 2) d2 = fmaf(u, e[i], d2);
+            else d3 = fmaf(u, e[i], d3);
+        }
+        const float dot = (d0 + d1) + (d2 + d3);
+        if (j & 1) s0 = fmaf(e[j], dot, s0); else s1 = fmaf(e[j], dot, s1);
+    }
+    return acc + (s0 + s1);
+}
+
+template <bool SPLIT, int FT, int KT, int NUMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UParam up, const WideParams wp) {
+    static_assert(FT > 0 && KT > 0 && 3 * KT <= 32 && FT >= NUMT, "built for the dataset shapes");
+    const Params& p = wp.p;
+    constexpr int H = SPLIT ? 2 : 1;
+    constexpr int CH = H * (int)X_HBW;                  // one K chunk of the activation buffer: hi [| lo] of 64 samples
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sX = base;
+    unsigned char* sW = base + p.oRing;
+    WideBars* bars = reinterpret_cast<WideBars*>(base + p.oMisc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = p.depth;
+    const uint32_t NS = (uint32_t)wp.ns;
+    const uint32_t rank = cluster_ctarank();            // 0 = leader
+    const bool leader = rank == 0;
+    const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
+    const int n_iter = wp.n_pair_tiles > cluster_id ? (wp.n_pair_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+    if (p.clk && threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.clk[blockIdx.x * FZ_NCLK + 28] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 29] = (long long)t;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS_MAX; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        mbar_init(&bars->x_ready, 2 * W_G);
+        mbar_init(&bars->x_free, 1);
+        mbar_init(&bars->x_free03, 1);
+        mbar_init(&bars->shallow_ready, W_G);
+        mbar_init(&bars->fin, 2 * 4);
+        for (int b = 0; b < 2; ++b) {
+            for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], W_EPI);
+            for (int j = 0; j < 2; ++j) mbar_init(&bars->acc_full[b][j], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int l = 0; l < L; ++l)
+            for (int h = 0; h < H; ++h) tma_prefetch_desc(&maps.w[l][h][0]);
+    }
+    const bool gather_warp = warp >= W_G0;
+    uint32_t tmem_base = 0;
+    if (gather_warp) {
+        cluster_arrive();                      // non-blocking: the gather starts on the batch at once
+    } else {
+        if (warp == W_MMA) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_holder)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR_COREW), "n"(CORE_THREADS) : "memory");
+        cluster_arrive(); cluster_wait();      // both CTAs' barriers and TMEM exist before anything crosses over
+        tc_fence_after();
+        tmem_base = bars->tmem_holder;
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
+    }
+
+    auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
+    auto layer_n = [&](int l) { return pad16(p.widths[l]); };
+
+    // Register budget per role (64 K per SM, 768 threads launched at 80): the gather group holds a sample's F values per thread
+    // through the FwFM interaction; the producer / issuer / idle warps and the epilogue give theirs up.  The pool is the CTA's own
+    // launch allocation (768 x 80 = 61,440; a larger total never gets its registers and the kernel hangs): 40 x 128 + 64 x 256 +
+    // 104 x 384 = 61,440.  (setmaxnreg sits at the head of each role's branch so that ptxas allocates that branch accordingly.)
+    if (warp < W_EPI0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp != W_MMA) {
+        // ================================================================= TMA producers (both CTAs): warps 0, 2, 3
+        // One warp gets a box out every ~390 cycles whatever its size or the ring depth (scripts/ubench/tma_ingest.cu: the
+        // try_wait -> expect_tx -> cp.async.bulk.tensor chain, not L2 latency or bytes), and a step of the issuer consumes two
+        // boxes per 768 cycles (bf16: one per 256).  So the boxes, numbered in consumption order, are dealt round-robin to three
+        // producer warps; box n lives in slot n mod NS.
+        const int pj = warp == 0 ? 0 : warp - 1;                  // 0, 1, 2
+        uint32_t n = 0;                                           // box counter
+        RingPos rp{0, 0};
+        for (int it = 0; it < n_iter; ++it) {
+            for (int l = 0; l < L; ++l) {
+                const int kch = (layer_k(l) + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
+                const int nstep = PT * kch;
+                for (int i = 0; i < nstep; ++i) {
+                    int pt, c;
+                    wide_step(i, PT, kch, pt, c);
+                    const int row0 = (2 * pt + (int)rank) * 128;          // rows past the matrix are zero-filled by TMA
+#pragma unroll
+                    for (int h = 0; h < H; ++h, ++n, rp.next(NS)) {
+                        if ((int)(n % N_PROD) != pj) continue;
+                        mbar_wait(&bars->empty[rp.s], rp.ph ^ 1, p.err, 12);
+                        const uint32_t f0 = mapa_u32(smem_u32(&bars->full[rp.s]), 0);
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(&bars->full[rp.s], 2u * STAGE_BYTES);     // both CTAs' boxes
+                            tma_load_2d_2cta(sW + (size_t)rp.s * STAGE_BYTES, &maps.w[l][h][0], f0, c * KCH, row0);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+      } else if (warp == W_MMA) {
+        // ================================================================= MMA issuer (leader only)
+        // Measured (scripts/ubench/mma_rate.cu): back-to-back N = 128 MMAs run at the 64-cycle math floor, and every
+        // tcgen05.commit in the stream costs the pipe ~100-190 cycles.  Interleaving the next step's barrier probes between the MMA
+        // groups made things worse (ptxas then spreads descriptor moves between the UTCHMMAs: 123 cycles per MMA), so the step
+        // stays a plain block: probes, then the MMAs back to back inside ONE elect-guarded region, then the commits.
+        if (leader) {
+            const uint32_t sW_u32 = smem_u32(sW), sX_u32 = smem_u32(sX);
+            const uint32_t idesc = make_idesc(256, 2 * TSW) | (1u << 16);     // B is MN-major
+            RingPos rp{0, 0};
+            uint32_t act_bits = 0;
+            int gl = 0;                                                      // global layer counter: accumulator parity
+            for (int it = 0; it < n_iter; ++it) {
+                for (int l = 0; l < L; ++l, ++gl) {
+                    const int buf = gl & 1;
+                    const int K = layer_k(l), kch = (K + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
+                    const int nstep = PT * kch, pt0_done = wide_pt0_done(PT, kch);
+                    const int x03_done = PT * (kch < 4 ? kch : 4) - 1;          // last step that reads chunks 0-3 of X
+                    for (int i = 0; i < nstep; ++i) {
+                        int pt, c;
+                        wide_step(i, PT, kch, pt, c);
+                        if (pt == 0) {
+                            if (l == 0) {
+                                if (c == 0) {
+                                    if (lane == 0 && it < 4) FZ_CLK(32 + 8 * it);
+                                    mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 21);
+                                    if (lane == 0 && it < 4) FZ_CLK(33 + 8 * it);
+                                }
+                            } else if ((c & 1) == 0) {
+                                const int g = c >> 1, bit = buf * MAX_MT + g;
+                                mbar_wait_cluster(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
+                                act_bits ^= 1u << bit;
+                            }
+                        }
+                        const int ks = min(4, (K - c * KCH) / 16);
+                        const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + pt * 128);
+                        const uint64_t bhi = make_desc_mn(sX_u32 + (uint32_t)(c * CH));
+                        const uint64_t blo = make_desc_mn(sX_u32 + (uint32_t)(c * CH) + X_HBW);
+                        const uint32_t acc0 = c ? 1u : 0u;
+                        RingPos s0 = rp, s1 = rp;
+                        if (SPLIT) s1.next(NS);
+                        const bool k0 = mbar_try(&bars->full[s0.s], s0.ph), k1 = SPLIT ? mbar_try(&bars->full[s1.s], s1.ph) : true;
+                        if (!k0) mbar_wait_cluster(&bars->full[s0.s], s0.ph, p.err, 24);
+                        if (!k1) mbar_wait_cluster(&bars->full[s1.s], s1.ph, p.err, 25);
+                        tc_fence_after();
+                        const uint64_t ah = make_desc_sw128(sW_u32 + s0.s * (uint32_t)STAGE_BYTES);
+                        const uint64_t al = make_desc_sw128(sW_u32 + s1.s * (uint32_t)STAGE_BYTES);
+                        if (elect_one()) {
+                            umma_bf16_2cta(dcol, ah, bhi, idesc, acc0);
+                            if (ks > 1) umma_bf16_2cta(dcol, ah + 2, bhi + 16, idesc, 1u);
+                            if (ks > 2) umma_bf16_2cta(dcol, ah + 4, bhi + 32, idesc, 1u);
+                            if (ks > 3) umma_bf16_2cta(dcol, ah + 6, bhi + 48, idesc, 1u);
+                            if (SPLIT) {
+                                umma_bf16_2cta(dcol, ah, blo, idesc, 1u);                 // W_hi X_lo
+                                if (ks > 1) umma_bf16_2cta(dcol, ah + 2, blo + 16, idesc, 1u);
+                                if (ks > 2) umma_bf16_2cta(dcol, ah + 4, blo + 32, idesc, 1u);
+                                if (ks > 3) umma_bf16_2cta(dcol, ah + 6, blo + 48, idesc, 1u);
+                            }
+                            umma_commit_2cta(&bars->empty[s0.s]);
+                            if (SPLIT) {
+                                umma_bf16_2cta(dcol, al, bhi, idesc, 1u);                 // W_lo X_hi
+                                if (ks > 1) umma_bf16_2cta(dcol, al + 2, bhi + 16, idesc, 1u);
+                                if (ks > 2) umma_bf16_2cta(dcol, al + 4, bhi + 32, idesc, 1u);
+                                if (ks > 3) umma_bf16_2cta(dcol, al + 6, bhi + 48, idesc, 1u);
+                                umma_commit_2cta(&bars->empty[s1.s]);
+                            }
+                            if (i == pt0_done) umma_commit_2cta(&bars->acc_full[buf][0]);
+                            if (PT > 1 && i == nstep - 1) umma_commit_2cta(&bars->acc_full[buf][1]);
+                            if (l == L - 1 && i == x03_done) umma_commit_2cta(&bars->x_free03);
+                            if (l == L - 1 && i == nstep - 1) umma_commit_2cta(&bars->x_free);
+                        }
+                        __syncwarp();
+                        rp = s1; rp.next(NS);
+                    }
+                    if (lane == 0 && it < 4 && l < 4) FZ_CLK(34 + 8 * it + l);
+                }
+            }
+        }
+      }
+    } else if (warp < W_G0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ================================================================= epilogue: set h = the samples of CTA h
+        const int h = (warp - W_EPI0) >> 2, q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(TSW * h);
+        const uint32_t xdst = mapa_u32(smem_u32(sX), (uint32_t)h);
+        const bool local = h == (int)rank;
+        uint32_t acc_bits = 0;
+        int gl = 0;
+        for (int it = 0; it < n_iter; ++it) {
+            const int par = it & 1;
+            float zsum[4] = {0.f, 0.f, 0.f, 0.f};         // lane pair (2 s, 2 s + 1): sample 16 blk + s of CTA h, summed over this warp's neurons
+            for (int l = 0; l < L; ++l, ++gl) {
+                const int buf = gl & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
+                const bool last = (l == L - 1);
+                float bb2[2], ff2[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int n = (2 * j + (int)rank) * 128 + row;
+                    const bool real = n < npad && n < N;
+                    bb2[j] = real ? __ldg(p.bias[l] + n) : 0.f;
+                    ff2[j] = (real && last) ? __ldg(p.fc + n) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j >= PT) break;
+                    const int bit = buf * 2 + j;
+                    mbar_wait(&bars->acc_full[buf][j], (acc_bits >> bit) & 1u, p.err, 31);
+                    acc_bits ^= 1u << bit;
+                    tc_fence_after();
+                    if (threadIdx.x == 32 * W_EPI0 && it < 2 && l < 4) FZ_CLK(64 + 16 * it + 4 * l + 2 * j);
+                    const int t = 2 * j + (int)rank;                    // this CTA's neuron tile of pair-tile j
+                    const int n = t * 128 + row;
+                    const int rows_valid = max(0, min(128, npad - t * 128));
+                    const float bb = bb2[j], ff = ff2[j];
+                    if (q4 * 32 < rows_valid) {
+                        const uint32_t xc = xdst + (uint32_t)((n >> 6) * CH + (n & 63) * 16);
+#pragma unroll
+                        for (int blk = 0; blk < 4; ++blk) {
+                            uint32_t d[16];
+                            tmem_ld16(taddr_row + (uint32_t)(buf * 256 + j * 128 + 16 * blk), d);
+                            tmem_ld_wait();
+                            if (last) {
+                                float v[16];
+#pragma unroll
+                                for (int s = 0; s < 16; ++s) v[s] = fmaxf(__uint_as_float(d[s]) + bb, 0.f) * ff;
+                                // transpose-reduce over the warp's 32 neurons: lane pair (2 s, 2 s + 1) ends with sample s
+#pragma unroll
+                                for (int off = 16, nn = 16; off >= 2; off >>= 1, nn >>= 1) {
+                                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                                    for (int i = 0; i < nn / 2; ++i) {
+                                        const float send = upper ? v[i] : v[i + nn / 2];
+                                        const float keep = upper ? v[i + nn / 2] : v[i];
+                                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                                    }
+                                }
+                                zsum[blk] += v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                            } else if (row < rows_valid) {
+#pragma unroll
+                                for (int g = 0; g < 2; ++g) {
+                                    uint32_t wh[4], wl[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float a0 = fmaxf(__uint_as_float(d[8 * g + 2 * i]) + bb, 0.f);
+                                        const float a1 = fmaxf(__uint_as_float(d[8 * g + 2 * i + 1]) + bb, 0.f);
+                                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);        // .x = a0 (low half)
+                                        wh[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                        if constexpr (SPLIT) {
+                                            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(wh[i] << 16),
+                                                                                              a1 - __uint_as_float(wh[i] & 0xffff0000u));
+                                            wl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                                        }
+                                    }
+                                    const uint32_t dst = xc + (uint32_t)(2 * blk + g) * X_SBO;
+                                    st_cluster_v4(dst, wh[0], wh[1], wh[2], wh[3]);
+                                    if constexpr (SPLIT) st_cluster_v4(dst + X_HBW, wl[0], wl[1], wl[2], wl[3]);
+                                }
+                            }
+                        }
+                    }
+                    if (!last && t * 128 < npad) {
+                        if (local) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->act_ready[(gl + 1) & 1][t]), 0));
+                    }
+                    if (threadIdx.x == 32 * W_EPI0 && it < 2 && l < 4) FZ_CLK(65 + 16 * it + 4 * l + 2 * j);
+                }
+            }
+            // this warp's partial sums of CTA h's 64 samples -> CTA h
+            if ((lane & 1) == 0) {
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk)
+                    st_cluster_f32(mapa_u32(smem_u32(&bars->red[par][rank][q4][16 * blk + (lane >> 1)]), (uint32_t)h), zsum[blk]);
+            }
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fin), (uint32_t)h));
+            if (warp == W_EPI0) {
+                // this CTA's samples of the tile: shallow part + the partial sums of both CTAs' neuron tiles
+                mbar_wait_cluster(&bars->fin, (uint32_t)par, p.err, 34);
+                mbar_wait(&bars->shallow_ready, (uint32_t)par, p.err, 33);
+                const long long ptile = cluster_id + (long long)it * n_clusters;
+                const long long b0 = (2 * ptile + rank) * TSW;
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int s = lane + 32 * s2;
+                    float z = bars->shallow[par][s];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) z += bars->red[par][r][q][s];
+                    if (b0 + s < p.B) {
+                        if (p.logits) p.logits[b0 + s] = z;
+                        if (p.prob) p.prob[b0 + s] = 1.0f / (1.0f + expf(-z));
+                    }
+                }
+                if (lane == 0 && it < 4) FZ_CLK(39 + 8 * it);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ================================================================= gather group: one tile ahead of the tensor pipe
+        const int gtid = threadIdx.x - 32 * W_G0, gw = warp - W_G0;
+        constexpr int FK = FT * KT, Kp = (FK + 15) & ~15, SPW = 32 / KT;        // SPW samples per warp and round
+        const ImgLayout IL = img_layout(FT, KT);
+        unsigned char* sImg = base + p.oImg;
+        float* sPart = reinterpret_cast<float*>(base + p.oPart);
+        float* sNum = reinterpret_cast<float*>(base + wp.oNum);
+        const EmbedParams& ep = p.ep;
+        // model state once per CTA: shallow image (descriptors, fwlw weights) and the numeric fields' single rows
+        for (uint32_t i = gtid; i < (uint32_t)(IL.total >> 4); i += G_THREADS_W) cp_async16(sImg + 16 * i, ep.image + 16 * i);
+        cp_async_wait_all();
+        group_sync<BAR_G>(G_THREADS_W);
+        const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg + IL.oHdr);
+        const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + IL.oFields);
+        const float* sWl = reinterpret_cast<const float*>(sImg + IL.oWl);
+        const bool plain = hdr->any_special == 0;
+        for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
+            const int f = i / KT, k = i - f * KT;
+            sNum[i] = __ldg((plain ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
+        }
+        group_sync<BAR_G>(G_THREADS_W);
+
+        const int sl = lane / KT, kk = lane - sl * KT;
+        const int slot = gw * SPW + sl;                         // sample of each half-tile this thread owns (0..31), if any
+        const bool owner = sl < SPW && slot < 32;
+        const bool fwlw = ep.flags & DFW_USE_FWLW;
+        constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
+        bool joined = false;
+        for (int it = 0; it < n_iter; ++it) {
+            const int par = it & 1;
+            const long long q = cluster_id + (long long)it * n_clusters;
+            const int64_t b0 = (2 * q + rank) * TSW;
+            const int64_t ba = b0 + slot, bb = b0 + 32 + slot;
+            const bool livea = owner && ba < ep.B, liveb = owner && bb < ep.B;
+            // ---- rows of this thread's two samples (32 + slot, then slot) into registers: one copy of the load code, all of it under
+            //      the previous tile's MLP
+            float e0[FT], e1[FT];
+#pragma unroll 1
+            for (int r = 1; r >= 0; --r) {
+                if (plain) wide_load<FT, KT, NUMT, true>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, e0);
+                else wide_load<FT, KT, NUMT, false>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, e0);
+                if (r) {
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) e1[f] = e0[f];
+                }
+            }
+            if (gtid == 0 && it < 4) FZ_CLK(96 + 8 * it);
+            if (!joined) {
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
+                cluster_wait();                             // set-up of both CTAs complete: barriers may be used
+                joined = true;
+            }
+            // ---- the tensor pipe releases X in two steps: chunks 0-3 after segment 2 of the previous tile's last layer, the rest
+            //      after its last MMA
+            if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
+            if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
+            if (owner) {
+                wide_write<SPLIT, FT, KT, 0, FSPLIT>(sX, slot, kk, e0);
+                wide_write<SPLIT, FT, KT, 0, FSPLIT>(sX, 32 + slot, kk, e1);
+            }
+            if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
+            if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
+            if (owner) {
+                wide_write<SPLIT, FT, KT, FSPLIT, FT>(sX, slot, kk, e0);
+                wide_write<SPLIT, FT, KT, FSPLIT, FT>(sX, 32 + slot, kk, e1);
+            }
+            // K padding columns [F*K, Kp) of all 64 samples are zero
+            for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
+                const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
+                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (sp >> 3) * X_SBO + (col & 63) * 16 + (sp & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
+                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(0.f);
+            }
+            fence_async_smem();                         // these stores are local
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
+            if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
+            // ---- first order + FwFM second order of both samples from the registers, under layer 1's MMAs (one copy of the code)
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                if (owner) {
+                    const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(ep, sF, r ? bb : ba, r ? liveb : livea, kk);
+                    sPart[kk * TSW + 32 * r + slot] = wide_interact<FT, KT>(e0, up, sWl, kk, fwlw, first);
+                }
+                if (r == 0) {
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) e0[f] = e1[f];
+                }
+            }
+            group_sync<BAR_G>(G_THREADS_W);
+            if (gtid < TSW) {
+                float tot = 0.f;
+#pragma unroll 1
+                for (int k = 0; k < KT; ++k) tot += sPart[k * TSW + gtid];
+                bars->shallow[par][gtid] = tot + __ldg(ep.bias);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->shallow_ready);
+            if (gtid == 0 && it < 4) FZ_CLK(99 + 8 * it);
+            group_sync<BAR_G>(G_THREADS_W);             // sPart is free for the next tile
+        }
+        if (!joined) {      // a pair without any tile still takes part in the set-up handshake
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
+            cluster_wait();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();        // neither CTA exits (or frees TMEM) while the other may still read its shared memory / TMEM
+    if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (p.clk && threadIdx.x == 32 * W_MMA) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.clk[blockIdx.x * FZ_NCLK + 30] = clock64(); p.clk[blockIdx.x * FZ_NCLK + 31] = (long long)t;
+    }
+}
+
+}  // namespace wd
+}  // namespace fz
+}  // namespace dfw

@@ -25,8 +25,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a broken pipeline traps (error to the host) instead of hanging the GPU.
+// Watchdog of the barrier waits: wall-clock, not spin count (one try_wait may suspend the thread for a while).  4 s is three
+// orders of magnitude above any legitimate wait of these kernels, profilers included.
+__device__ __forceinline__ unsigned long long watchdog_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool watchdog_expired(unsigned long long& t0) {
+    const unsigned long long t = watchdog_now();
+    if (t0 == 0) { t0 = t; return false; }
+    return t - t0 > 4000000000ull;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
     const uint32_t addr = smem_u32(bar);
+    unsigned long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
         asm volatile(
@@ -35,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
-        if (spin > (1u << 28)) {     // ~10 s: only a broken pipeline gets here (profilers and debuggers stretch waits a lot)
+        if ((spin & 0x3ffu) == 0x3ffu && watchdog_expired(t0)) {     // only a broken pipeline gets here
             if (err) atomicExch(err, code);
             __trap();
         }
