@@ -227,13 +227,12 @@ int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const fl
                             int precision, void* workspace, size_t workspace_bytes, float* logits_host, float* prob_host,
                             void* stream);
 /* Transport dfw_forward_host_stream will use for these buffers.  1 = "mapped": every buffer is pinned host memory the device
- * can address (cudaHostAlloc / cudaHostRegister under unified addressing) and the fused kernel takes the model.  Kernels then
- * move the bytes over PCIe themselves: a pull kernel (small CTAs on a high-priority stream, co-resident with the compute CTAs)
- * brings each batch's Xi / Xv into a device staging slot ahead of the fused kernel, whose epilogue stores logits /
- * probabilities straight into host memory -- two launches per batch, no copy-engine calls.  0 = "staged": cudaMemcpyAsync
- * H2D -> kernels -> D2H per batch (pageable buffers, models outside the fused kernel's shapes).  Results are bit-identical.
- * DFW_HOST_TRANSPORT=copy|mapped in the environment forces one (mapped then fails with DFW_E_UNSUPPORTED where it cannot
- * run); mapped_direct is a debug form in which the fused kernel's gather warps read the host buffers themselves. */
+ * can address (cudaHostAlloc / cudaHostRegister under unified addressing) and the fused kernel takes the model.  Xi / Xv then
+ * travel in CHUNKS of up to 8 batches per copy-engine transfer (SM-issued loads from host memory saturate at ~34 GB/s on B200
+ * boxes, the copy engine reaches ~55 GB/s once a transfer is a few MB) into rotating staging slots, the fused kernels of a
+ * chunk's batches wait on the chunk's event, and their epilogues store logits / probabilities straight into the pinned host
+ * buffers -- one launch per batch, no D2H copies.  0 = "staged": cudaMemcpyAsync H2D -> kernels -> D2H per batch (pageable
+ * buffers, models outside the fused kernel's shapes).  Results are bit-identical. */
 int dfw_host_transport_is_mapped(const dfw_model* m, int precision, const void* xi_host, const void* xv_host,
                                  const void* logits_host, const void* prob_host);
 

@@ -15,7 +15,8 @@ from test_module_cpu import build
 pytestmark = pytest.mark.gpu
 FP32_REL = 1e-5
 BF16_REL = 5e-4           # bf16 path, logit-relative: holds wherever the shallow (fp32) term sets the logit scale (configs 1-4)
-BF16_DEEP_REL = 1.2e-2    # bf16 path in general: the whole error is the MLP's operand rounding, <= 1.2e-2 * max|deep| (measured <= 9.1e-3)
+BF16_DEEP_REL = 2.5e-2    # bf16 path in general: the whole error is the MLP's operand rounding, <= 2.5e-2 * max|deep| (measured: <= 9.1e-3 on
+                          # the golden cases, 1.33e-2 / 1.74e-2 on 136- / 512-wide two-layer MLPs whose deep term is only ~0.5)
 
 
 def to_cuda(cfg, weights, **kw):

@@ -226,13 +226,17 @@ extern "C" int dfw_forward_host(const dfw_model* m, const int64_t* xi_host, cons
 namespace {
 constexpr int kSlots = 3;      // staged transport: slots of the device workspace = streams in rotation
 constexpr int kLanes = 6;      // mapped transport: compute streams in rotation
-constexpr int kStage = 6;      // mapped transport: input staging slots (Xi + Xv of one batch each) at the front of the workspace
+constexpr int kStage = 6;      // mapped transport, pull-kernel form (debug builds): staging slots of one batch each
+constexpr int kChunk = 8;      // mapped transport: batches per copy-engine transfer (a chunk); the first chunks of a call are 1, 2, 4
+constexpr int kChunkSlots = 3; // mapped transport: chunk-sized staging slots in rotation
 struct HostPipe {
     cudaStream_t streams[kLanes] = {};
     cudaEvent_t done[kLanes] = {};
     cudaEvent_t start = nullptr;
     cudaStream_t pull = nullptr;                    // high priority: the PCIe pull of batch i + 1 runs under the kernels of batch i
     cudaEvent_t staged[kStage] = {}, freed[kStage] = {};
+    cudaStream_t copy = nullptr;                    // chunked H2D transfers of the mapped transport
+    cudaEvent_t chunk_in[kChunkSlots] = {}, chunk_free[kChunkSlots][kLanes] = {};
     int device = -1;
 };
 thread_local HostPipe g_pipe[8];
@@ -254,6 +258,11 @@ int get_pipe(HostPipe** out) {
         for (int i = 0; i < kStage; ++i) {
             DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.staged[i], cudaEventDisableTiming));
             DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.freed[i], cudaEventDisableTiming));
+        }
+        DFW_CUDA_OK(cudaStreamCreateWithPriority(&hp.copy, cudaStreamNonBlocking, hi_prio));
+        for (int i = 0; i < kChunkSlots; ++i) {
+            DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.chunk_in[i], cudaEventDisableTiming));
+            for (int l = 0; l < kLanes; ++l) DFW_CUDA_OK(cudaEventCreateWithFlags(&hp.chunk_free[i][l], cudaEventDisableTiming));
         }
         hp.device = dev;
     }
@@ -300,7 +309,10 @@ extern "C" int dfw_host_transport_is_mapped(const dfw_model* m, int precision, c
 
 extern "C" size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, int64_t batch, int precision) {
     if (!m || batch <= 0) return 256;
-    return kSlots * align_up(host_layout(m, batch, precision).total, 256);
+    const HostLayout H = host_layout(m, batch, precision);
+    const size_t staged = kSlots * align_up(H.total, 256);
+    const size_t mapped = (size_t)kChunkSlots * kChunk * H.oLogit;          // mapped transport: 3 staging slots of kChunk batches (Xi + Xv)
+    return staged > mapped ? staged : mapped;
 }
 
 extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t N,
@@ -334,6 +346,67 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
         float* prob_d = static_cast<float*>(mapped_alias(prob_host));
         const bool direct = host_transport_override() == 3;
         const size_t stage_bytes = H.oLogit;            // the Xi + Xv part of a slot
+        if (host_transport_override() == 0 && workspace_bytes >= 2 * stage_bytes) {
+            // Default form.  Measured: SM-issued loads from pinned host memory saturate at ~34 GB/s on these boxes whatever the
+            // kernel (the round-1 pull kernel, or the fused kernel reading host memory itself), while the copy engine reaches
+            // ~55 GB/s -- once a transfer is a few MB, a single batch (1.06 MB) pays ~8 us of set-up per copy.  So Xi / Xv travel
+            // in CHUNKS of up to kChunk batches (8.5 MB) on one copy stream into kChunkSlots rotating staging slots; the fused
+            // kernels of a chunk's batches (one launch each, kLanes streams) wait on the chunk's event, read HBM and store their
+            // probabilities / logits straight into the pinned host buffers.  The first chunks of a call are 1, 2 and 4 batches so
+            // that the pipeline fills quickly.
+            int chunk_cap = (int)(workspace_bytes / (kChunkSlots * stage_bytes));
+            if (chunk_cap > kChunk) chunk_cap = kChunk;
+            int nslots = kChunkSlots;
+            if (chunk_cap < 1) { chunk_cap = 1; nslots = (int)(workspace_bytes / stage_bytes); if (nslots > kChunkSlots) nslots = kChunkSlots; }
+            const size_t slot_bytes = (size_t)chunk_cap * stage_bytes;
+            const size_t xi_b = (size_t)batch * C * ib, xv_b = (size_t)batch * num * sizeof(float);
+            DFW_CUDA_OK(cudaStreamWaitEvent(hp->copy, hp->start, 0));
+            int64_t done = 0, bi = 0;
+            int lane_rr = 0;
+            bool lane_touched[kChunkSlots][kLanes] = {};
+            for (int64_t k = 0; done < N; ++k) {
+                const int slot = (int)(k % nslots);
+                int g = k < 3 ? (1 << k) : chunk_cap;                      // 1, 2, 4, then full chunks
+                if (g > chunk_cap) g = chunk_cap;
+                const int64_t left = N - done;
+                int64_t nb = (left + batch - 1) / batch;
+                if (nb > g) nb = g;
+                const int64_t rows = nb * batch < left ? nb * batch : left;
+                char* ws = static_cast<char*>(workspace) + (size_t)slot * slot_bytes;
+                char* xi_dev = ws;                                         // [nb x Xi][nb x Xv]: each batch's Xi / Xv contiguous
+                char* xv_dev = ws + (size_t)chunk_cap * align_up(xi_b, 256);
+                if (k >= nslots)                                            // the slot's previous chunk has been consumed by every lane that ran it
+                    for (int l = 0; l < kLanes; ++l)
+                        if (lane_touched[slot][l]) DFW_CUDA_OK(cudaStreamWaitEvent(hp->copy, hp->chunk_free[slot][l], 0));
+                if (C > 0) DFW_CUDA_OK(cudaMemcpyAsync(xi_dev, xi_d + (size_t)done * C * ib, (size_t)rows * C * ib, cudaMemcpyHostToDevice, hp->copy));
+                if (num > 0) DFW_CUDA_OK(cudaMemcpyAsync(xv_dev, xv_d + (size_t)done * num * sizeof(float), (size_t)rows * num * sizeof(float), cudaMemcpyHostToDevice, hp->copy));
+                DFW_CUDA_OK(cudaEventRecord(hp->chunk_in[slot], hp->copy));
+                for (int l = 0; l < kLanes; ++l) lane_touched[slot][l] = false;
+                for (int64_t j = 0; j < nb; ++j, ++bi) {
+                    const int64_t off = j * batch;
+                    const int64_t b = rows - off < batch ? rows - off : batch;
+                    const int ln = lane_rr;
+                    lane_rr = (lane_rr + 1) % kLanes;
+                    cudaStream_t lane = hp->streams[ln];
+                    if (!lane_touched[slot][ln]) DFW_CUDA_OK(cudaStreamWaitEvent(lane, hp->chunk_in[slot], 0));
+                    lane_touched[slot][ln] = true;
+                    if (int rc = dfw_forward_fused(m, reinterpret_cast<const int64_t*>(xi_dev + (size_t)off * C * ib), C, 1,
+                                                   reinterpret_cast<const float*>(xv_dev + (size_t)off * num * sizeof(float)), num, 1, b,
+                                                   precision, logit_d ? logit_d + done + off : nullptr, prob_d ? prob_d + done + off : nullptr,
+                                                   nullptr, lane))
+                        return rc;
+                }
+                for (int l = 0; l < kLanes; ++l)
+                    if (lane_touched[slot][l]) DFW_CUDA_OK(cudaEventRecord(hp->chunk_free[slot][l], hp->streams[l]));
+                done += rows;
+            }
+            for (int i = 0; i < kLanes; ++i) {
+                DFW_CUDA_OK(cudaEventRecord(hp->done[i], hp->streams[i]));
+                DFW_CUDA_OK(cudaStreamWaitEvent(main_st, hp->done[i], 0));
+            }
+            DFW_CUDA_OK(cudaStreamSynchronize(main_st));
+            return 0;
+        }
         // as many staging slots as the workspace holds (it is sized for the staged transport's 3 full slots: at least 3 fit)
         const int nstage = (int)(workspace_bytes / stage_bytes < (size_t)kStage ? workspace_bytes / stage_bytes : (size_t)kStage);
         DFW_REQUIRE(direct || nstage >= 2, DFW_E_WORKSPACE, "workspace too small for two staging slots");

@@ -795,7 +795,9 @@ static bool make_plan_wide(const dfw_model* m, bool split, const Plan& pl, wd::W
     size_t o = ((size_t)p.x_chunks * CH + 1023) / 1024 * 1024;
     p.oE = 0;
     p.oRing = (uint32_t)o;
-    const size_t img = up16(img_layout(F, K).total), part = up16(sizeof(float) * K * wd::TSW), nrow = up16(sizeof(float) * (num > 0 ? num : 1) * K);
+    // compact copy of the shallow image: header | fwlw weights | field descriptors (fused_wide.cuh)
+    const size_t img = 16 + up16(sizeof(float) * F * K) + up16(sizeof(dfw_field_desc) * F);
+    const size_t part = up16(sizeof(float) * K * wd::TSW), nrow = up16(sizeof(float) * (num > 0 ? num : 1) * K);
     const size_t tail = img + part + nrow + up16(sizeof(wd::WideBars)) + 64;
     if (o + tail + 1024 + 2 * (size_t)STAGE_BYTES > SMEM_LIMIT) return false;
     int ns = (int)((SMEM_LIMIT - 1024 - o - tail) / STAGE_BYTES);
@@ -805,6 +807,19 @@ static bool make_plan_wide(const dfw_model* m, bool split, const Plan& pl, wd::W
         if (cap >= 2 && cap < ns) ns = cap;
     }
     if (ns < (split ? 4 : 2)) return false;
+    // grouped ring (one full / empty barrier and ONE tcgen05.commit per two boxes): bf16x3 pairs a step's hi and lo box; bf16
+    // pairs two steps, which needs an even number of boxes per tile so that no group is left half filled at the end
+    long long boxes = 0;
+    {
+        int k = p.in_dim;
+        for (int l = 0; l < p.depth; ++l) {
+            boxes += (long long)((n_mtiles(pad16(p.widths[l])) + 1) / 2) * ((pad16(k) + KCH - 1) / KCH);
+            k = p.widths[l];
+        }
+    }
+    static const int grp_env = env_int("DFW_WIDE_GRP", 2);
+    wp.grp = (grp_env == 2 && ns >= 4 && (split || boxes % 2 == 0)) ? 2 : 1;
+    if (wp.grp == 2) ns &= ~1;
     wp.ns = ns;
     o += (size_t)ns * STAGE_BYTES; p.oImg = (uint32_t)o;
     o += img;                       p.oPart = (uint32_t)o;
@@ -824,6 +839,7 @@ static int launch_wide(const dfw_model* m, const Plan& pl, Maps& maps, cudaStrea
     if (!make_plan_wide(m, SPLIT, pl, wp, smem_bytes)) return 0;
     taken = true;
     wp.p.cluster = 2;
+    wp.dbg = env_int("DFW_WIDE_DBG", 0);
     if (int rc = get_maps(m, SPLIT, 1, wp.p.in_dim, maps)) return rc;    // whole 128-row boxes: each CTA loads its own tile
     auto kern = wd::fused_wide_kernel<SPLIT, FT, KT, NUMT>;
     static thread_local bool configured_dev[16] = {};       // per device: function attributes are per context

@@ -38,7 +38,7 @@ namespace fz {
 namespace wd {
 
 constexpr int TSW = 64;                        // samples per CTA and tile
-constexpr int W_MMA = 1, N_PROD = 3;          // producers: warps 0, 2, 3
+constexpr int W_MMA = 3, N_PROD = 3;          // producers: warps 0, 1, 2
 constexpr int W_EPI0 = 4, W_EPI = 8;
 constexpr int W_G0 = W_EPI0 + W_EPI, W_G = 12;
 constexpr int THREADS = 32 * (W_G0 + W_G);     // 768: 80 registers per thread
@@ -60,14 +60,17 @@ struct WideBars {
     uint64_t fin;                    // per CTA: the partial sums of its samples are in `red` (2 x 4 arrives per tile)
     uint32_t tmem_holder, pad_;
     float shallow[2][TSW];           // [tile parity]
-    float red[2][2][4][TSW];         // [tile parity][source CTA][lane quarter][sample]
+    float red[2][4][TSW];            // [source CTA][lane quarter][sample] (one buffer: a warp writes tile t + 1 only after every
+                                     // epilogue warp of the pair, the finisher included, has passed tile t -- act_ready couples them)
 };
 
 struct WideParams {
     Params p;
     int n_pair_tiles;                // ceil(ceil(B / 64) / 2)
-    int ns;                          // ring slots
+    int ns;                          // ring slots (16 KB each)
+    int grp;                         // slots per full / empty barrier: 2 = one barrier pair (and ONE tcgen05.commit) per two boxes
     uint32_t oNum;                   // (num, K) floats: the single row of every numeric field, fetched once per CTA
+    int dbg;                         // -DDFW_DEBUG builds only (timeline experiments; 0 otherwise and the code is compiled out)
 };
 
 // step i of a layer's MMA sequence -> (pair-tile, chunk); see the header: [0: 0..sp)[1: 0..sp)[0: sp..kch)[1: sp..kch)
@@ -99,14 +102,45 @@ __device__ __forceinline__ uint32_t load_index_lo(const EmbedParams& p, int64_t 
     return (uint32_t)__ldg(reinterpret_cast<const int32_t*>(p.xi) + 2 * elem);          // little endian
 }
 
-template <int FT, int KT, int NUMT, bool PLAIN>
-__device__ __forceinline__ void wide_load(const EmbedParams& ep, const dfw_field_desc* sF, const float* sNum, int64_t b,
-                                          bool live, int kk, float (&e)[FT]) {
-    constexpr int CT = FT - NUMT;
-    if (live) {
-        uint32_t idx[CT > 0 ? CT : 1];
+// the categorical indices of global sample b, raw low words (no model state needed: these loads are issued first).  Contiguous
+// rows (xi_sc == 1: what forward() and the host path pass) are read with 16- / 8-byte loads at constant offsets -- the strided
+// form costs ~25 instructions of 64-bit address arithmetic per index.
+template <int CT>
+__device__ __forceinline__ void wide_idx(const EmbedParams& ep, int64_t b, bool live, uint32_t (&idx)[CT]) {
+    if (!live) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) idx[c] = 0u;
+        return;
+    }
+    const bool i32 = ep.flags & DFW_XI_INT32;
+    const char* row = reinterpret_cast<const char*>(ep.xi) + b * ep.xi_sb * (i32 ? 4 : 8);
+    if (ep.xi_sc == 1 && !i32 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(row);              // two int64 per load: low words .x and .z
+#pragma unroll
+        for (int c = 0; c + 1 < CT; c += 2) {
+            const uint4 v = __ldg(r4 + (c >> 1));
+            idx[c] = v.x; idx[c + 1] = v.z;
+        }
+        if (CT & 1) idx[CT - 1] = __ldg(reinterpret_cast<const uint32_t*>(row) + 2 * (CT - 1));
+    } else if (ep.xi_sc == 1 && i32 && (reinterpret_cast<uintptr_t>(row) & 7) == 0) {
+        const uint2* r2 = reinterpret_cast<const uint2*>(row);
+#pragma unroll
+        for (int c = 0; c + 1 < CT; c += 2) {
+            const uint2 v = __ldg(r2 + (c >> 1));
+            idx[c] = v.x; idx[c + 1] = v.y;
+        }
+        if (CT & 1) idx[CT - 1] = __ldg(reinterpret_cast<const uint32_t*>(row) + (CT - 1));
+    } else {
 #pragma unroll
         for (int c = 0; c < CT; ++c) idx[c] = load_index_lo(ep, b * ep.xi_sb + c * ep.xi_sc);
+    }
+}
+
+template <int FT, int KT, int NUMT, bool PLAIN>
+__device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field_desc* sF, const float* sNum, int64_t b,
+                                          bool live, int kk, uint32_t (&idx)[FT - NUMT > 0 ? FT - NUMT : 1], float (&e)[FT]) {
+    constexpr int CT = FT - NUMT;
+    if (live) {
         if (ep.err) {       // DFW_CHECK_INDEX: the full 64-bit value must be inside the table
 #pragma unroll 1
             for (int c = 0; c < CT; ++c) {
@@ -134,6 +168,8 @@ __device__ __forceinline__ void wide_load(const EmbedParams& ep, const dfw_field
                 }
             }
         }
+        const float* xrow = ep.xv + b * ep.xv_sb;
+        const int64_t xsc = ep.xv_sc;
 #pragma unroll
         for (int f = 0; f < NUMT; ++f) {
             float v = sNum[f * KT + kk];
@@ -142,7 +178,7 @@ __device__ __forceinline__ void wide_load(const EmbedParams& ep, const dfw_field
                 if (op == DFW_TABLE_QR_MULT) v *= __ldg(sF[f].w2_r + kk);
                 else if (op == DFW_TABLE_QR_ADD) v += __ldg(sF[f].w2_r + kk);
             }
-            e[f] = v * ep.xv[b * ep.xv_sb + f * ep.xv_sc];
+            e[f] = v * (xsc == 1 ? __ldg(xrow + f) : __ldg(xrow + f * xsc));
         }
     } else {
 #pragma unroll
@@ -180,11 +216,12 @@ __device__ __forceinline__ float wide_first(const EmbedParams& ep, const dfw_fie
     return acc;
 }
 
-// bf16 (hi | lo) operand columns of fields [F0, F1) of tile-local sample s:  element (k = f * KT + kk, s) lives at
-// (k / 64) * CH + (s / 8) * X_SBO + (k % 64) * 16 + (s % 8) * 2  (+ X_HBW for the lo part).  With f unrolled everything but "does
-// f * KT + kk cross into the next 64-wide chunk" is a compile-time constant.
+// bf16 (hi | lo) operand columns of fields [F0, F1) of the ADJACENT tile-local samples s (even) and s + 1:  element (k = f * KT + kk,
+// s) lives at (k / 64) * CH + (s / 8) * X_SBO + (k % 64) * 16 + (s % 8) * 2  (+ X_HBW for the lo part), so the two samples share a
+// 32-bit word: one cvt.rn.bf16x2 and one store per field and part.  With f unrolled everything but "does f * KT + kk cross into
+// the next 64-wide chunk" is a compile-time constant.
 template <bool SPLIT, int FT, int KT, int F0, int F1>
-__device__ __forceinline__ void wide_write(unsigned char* sX, int s, int kk, const float (&e)[FT]) {
+__device__ __forceinline__ void wide_write2(unsigned char* sX, int s, int kk, const float (&ea)[FT], const float (&eb)[FT]) {
     constexpr int CH = (SPLIT ? 2 : 1) * (int)X_HBW, JUMP = CH - 64 * 16;
     unsigned char* const xbase = sX + (s >> 3) * X_SBO + (s & 7) * 2 + kk * 16;
 #pragma unroll
@@ -193,9 +230,13 @@ __device__ __forceinline__ void wide_write(unsigned char* sX, int s, int kk, con
         int off = c0 * 16 + (c0 >> 6) * JUMP;
         if (lo + KT > 64) off += (kk >= 64 - lo) ? JUMP : 0;
         unsigned char* dst = xbase + off;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(e[f]);
-        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
-        if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(e[f] - __bfloat162float(hi));
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(ea[f], eb[f]);        // .x = sample s (low half)
+        const uint32_t wh = *reinterpret_cast<const uint32_t*>(&h2);
+        *reinterpret_cast<uint32_t*>(dst) = wh;
+        if constexpr (SPLIT) {
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(ea[f] - __uint_as_float(wh << 16), eb[f] - __uint_as_float(wh & 0xffff0000u));
+            *reinterpret_cast<uint32_t*>(dst + X_HBW) = *reinterpret_cast<const uint32_t*>(&l2);
+        }
     }
 }
 
@@ -256,7 +297,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS_MAX; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+        for (int s = 0; s < NS_MAX; ++s) { mbar_init(&bars->full[s], (uint32_t)wp.grp); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->x_ready, 2 * W_G);
         mbar_init(&bars->x_free, 1);
         mbar_init(&bars->x_free03, 1);
@@ -270,7 +311,14 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         for (int l = 0; l < L; ++l)
             for (int h = 0; h < H; ++h) tma_prefetch_desc(&maps.w[l][h][0]);
     }
-    const bool gather_warp = warp >= W_G0;
+    // Roles by warp id.  A warp's scheduler is warp % 4, and a warpgroup (setmaxnreg granule) is four consecutive warps, i.e. one
+    // per scheduler.  Scheduler 3 is kept for the MMA issuer: besides it only two epilogue warps and the three TMA producers
+    // live there, all of which sleep most of the time; the twelve gather warps are the other three members of warpgroups 0, 3, 4, 5.
+    //   3              MMA issuer            0-2, 12-14, 16-18, 20-22   gather group (gw = 0..11)
+    //   4-11           epilogue              15, 19, 23                 TMA producers
+    const bool epi_warp = warp >= W_EPI0 && warp < W_G0;
+    const bool prod_warp = warp >= W_G0 && (warp & 3) == 3;
+    const bool gather_warp = !epi_warp && !prod_warp && warp != W_MMA;
     uint32_t tmem_base = 0;
     if (gather_warp) {
         cluster_arrive();                      // non-blocking: the gather starts on the batch at once
@@ -290,19 +338,143 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
     auto layer_k = [&](int l) { return pad16(l == 0 ? p.in_dim : p.widths[l - 1]); };
     auto layer_n = [&](int l) { return pad16(p.widths[l]); };
 
-    // Register budget per role (64 K per SM, 768 threads launched at 80): the gather group holds a sample's F values per thread
-    // through the FwFM interaction; the producer / issuer / idle warps and the epilogue give theirs up.  The pool is the CTA's own
-    // launch allocation (768 x 80 = 61,440; a larger total never gets its registers and the kernel hangs): 40 x 128 + 64 x 256 +
-    // 104 x 384 = 61,440.  (setmaxnreg sits at the head of each role's branch so that ptxas allocates that branch accordingly.)
-    if (warp < W_EPI0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      if (warp != W_MMA) {
-        // ================================================================= TMA producers (both CTAs): warps 0, 2, 3
+    auto gather_role = [&]() __attribute__((always_inline)) {
+        // ================================================================= gather group: one tile ahead of the tensor pipe
+        const int gw = warp < W_MMA ? warp : 3 + (warp - W_G0) - ((warp - W_G0) >> 2);      // 0..11
+        const int gtid = 32 * gw + lane;
+        constexpr int FK = FT * KT, Kp = (FK + 15) & ~15;
+        const ImgLayout IL = img_layout(FT, KT);
+        unsigned char* sImg = base + p.oImg;
+        float* sPart = reinterpret_cast<float*>(base + p.oPart);
+        float* sNum = reinterpret_cast<float*>(base + wp.oNum);
+        const EmbedParams& ep = p.ep;
+        // model state once per CTA: header, fwlw weights and field descriptors of the shallow image (U and the pair list stay in
+        // global memory: the field matrix is a kernel parameter here) and the numeric fields' single rows
+        constexpr uint32_t W_WL = 16, W_FIELDS = W_WL + (uint32_t)up16(sizeof(float) * FT * KT);
+        if (gtid == 0) cp_async16(sImg, ep.image + IL.oHdr);
+        for (uint32_t i = gtid; i < (uint32_t)(up16(sizeof(float) * FT * KT) >> 4); i += G_THREADS_W)
+            cp_async16(sImg + W_WL + 16 * i, ep.image + IL.oWl + 16 * i);
+        for (uint32_t i = gtid; i < (uint32_t)(up16(sizeof(dfw_field_desc) * FT) >> 4); i += G_THREADS_W)
+            cp_async16(sImg + W_FIELDS + 16 * i, ep.image + IL.oFields + 16 * i);
+        const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg);
+        const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + W_FIELDS);
+        const float* sWl = reinterpret_cast<const float*>(sImg + W_WL);
+
+        // A thread owns column kk of TWO ADJACENT samples (they share a 32-bit word of the operand); a warp holds three such pairs:
+        // 32 pairs per tile on 12 x 3 places.
+        constexpr int CT = FT - NUMT > 0 ? FT - NUMT : 1;
+        const int sl = lane / KT, kk = lane - sl * KT;
+        const int slot = 3 * gw + sl;
+        const bool owner = sl < 3 && slot < 32;
+        const int sa = 2 * slot;                                // tile-local samples sa, sa + 1
+        const bool fwlw = ep.flags & DFW_USE_FWLW;
+        constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
+        bool joined = false, plain = true;
+        for (int it = 0; it < n_iter; ++it) {
+            const int par = it & 1;
+            const long long q = cluster_id + (long long)it * n_clusters;
+            const int64_t b0 = (2 * q + rank) * TSW;
+            const int64_t ba = b0 + sa, bb = ba + 1;
+            const bool livea = owner && ba < ep.B, liveb = owner && bb < ep.B;
+            // ---- indices, then rows, of this thread's two samples into registers, all of it under the previous tile's MLP (first
+            //      tile: the first index loads fly under the model-state copy)
+            float e0[FT], e1[FT];
+#pragma unroll 1
+            for (int r = 1; r >= 0; --r) {          // one copy of the load code; 26 + 26 loads in flight per pass (two passes in flight
+                                                    // at once cost more in spilled registers than they gain: 24 k against 12 k cycles)
+                uint32_t ix[CT];
+                wide_idx<CT>(ep, r ? bb : ba, r ? liveb : livea, ix);
+                if (it == 0 && r == 1) {
+                    cp_async_wait_all();
+                    group_sync<BAR_G>(G_THREADS_W);                 // header, fwlw weights, descriptors are in shared memory
+                    plain = hdr->any_special == 0;
+                    for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
+                        const int f = i / KT, k = i - f * KT;
+                        sNum[i] = __ldg((plain ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
+                    }
+                    group_sync<BAR_G>(G_THREADS_W);
+                }
+                if (plain) wide_rows<FT, KT, NUMT, true>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, ix, e0);
+                else wide_rows<FT, KT, NUMT, false>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, ix, e0);
+                if (r) {
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) e1[f] = e0[f];
+                }
+            }
+            if (gtid == 0 && it < 4) FZ_CLK(96 + 8 * it);
+            if (!joined) {
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
+                cluster_wait();                             // set-up of both CTAs complete: barriers may be used
+                joined = true;
+            }
+            // ---- the tensor pipe releases X in two steps: chunks 0-3 after segment 2 of the previous tile's last layer, the rest
+            //      after its last MMA
+            if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
+            if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
+            if (owner) wide_write2<SPLIT, FT, KT, 0, FSPLIT>(sX, sa, kk, e0, e1);
+            if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
+            if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
+            if (owner) wide_write2<SPLIT, FT, KT, FSPLIT, FT>(sX, sa, kk, e0, e1);
+            // K padding columns [F*K, Kp) of all 64 samples are zero
+            for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
+                const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
+                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (sp >> 3) * X_SBO + (col & 63) * 16 + (sp & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
+                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(0.f);
+            }
+            fence_async_smem();                         // these stores are local
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
+            if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
+            // ---- first order + FwFM second order of both samples from the registers, under layer 1's MMAs (one copy of the code)
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+#ifdef DFW_DEBUG
+                const bool dbg_skip = (wp.dbg & 2) || ((wp.dbg & 1) && (warp & 3) == 1);       // WRONG logits: timeline experiments only
+#else
+                constexpr bool dbg_skip = false;
+#endif
+                if (owner && !dbg_skip) {
+                    const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(ep, sF, r ? bb : ba, r ? liveb : livea, kk);
+                    sPart[kk * TSW + sa + r] = wide_interact<FT, KT>(e0, up, sWl, kk, fwlw, first);
+                }
+                if (r == 0) {
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) e0[f] = e1[f];
+                }
+            }
+            group_sync<BAR_G>(G_THREADS_W);
+            if (gtid < TSW) {
+                float tot = 0.f;
+#pragma unroll 1
+                for (int k = 0; k < KT; ++k) tot += sPart[k * TSW + gtid];
+                bars->shallow[par][gtid] = tot + __ldg(ep.bias);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->shallow_ready);
+            if (gtid == 0 && it < 4) FZ_CLK(99 + 8 * it);
+            group_sync<BAR_G>(G_THREADS_W);             // sPart is free for the next tile
+        }
+        if (!joined) {      // a pair without any tile still takes part in the set-up handshake
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
+            cluster_wait();
+        }
+    };
+
+    // Register budget (64 K per SM, 768 threads launched at 80; the pool is the CTA's own launch allocation 768 x 80 = 61,440 -- a
+    // larger total never gets its registers and the kernel hangs): warpgroups 1-2 (epilogue) give up 16 registers per thread,
+    // warpgroups 0, 3, 4, 5 (gather + issuer / producer) take 8: 64 x 256 + 88 x 512 = 61,440.  setmaxnreg sits at the head of the
+    // two branches so that ptxas allocates each accordingly.
+    if (!epi_warp) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+      if (prod_warp) {
+        // ================================================================= TMA producers (both CTAs): warps 15, 19, 23
         // One warp gets a box out every ~390 cycles whatever its size or the ring depth (scripts/ubench/tma_ingest.cu: the
         // try_wait -> expect_tx -> cp.async.bulk.tensor chain, not L2 latency or bytes), and a step of the issuer consumes two
         // boxes per 768 cycles (bf16: one per 256).  So the boxes, numbered in consumption order, are dealt round-robin to three
         // producer warps; box n lives in slot n mod NS.
-        const int pj = warp == 0 ? 0 : warp - 1;                  // 0, 1, 2
+        const int pj = (warp - W_G0) >> 2;                        // 0, 1, 2
+        const uint32_t GRP = (uint32_t)wp.grp;                    // slots s, s + 1 share full / empty barrier s / GRP
         uint32_t n = 0;                                           // box counter
         RingPos rp{0, 0};
         for (int it = 0; it < n_iter; ++it) {
@@ -316,11 +488,19 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
 #pragma unroll
                     for (int h = 0; h < H; ++h, ++n, rp.next(NS)) {
                         if ((int)(n % N_PROD) != pj) continue;
-                        mbar_wait(&bars->empty[rp.s], rp.ph ^ 1, p.err, 12);
-                        const uint32_t f0 = mapa_u32(smem_u32(&bars->full[rp.s]), 0);
+                        const uint32_t g = rp.s / GRP;
+                        mbar_wait(&bars->empty[g], rp.ph ^ 1, p.err, 12);
+                        const uint32_t f0 = mapa_u32(smem_u32(&bars->full[g]), 0);
                         if (elect_one()) {
-                            if (leader) mbar_expect_tx(&bars->full[rp.s], 2u * STAGE_BYTES);     // both CTAs' boxes
-                            tma_load_2d_2cta(sW + (size_t)rp.s * STAGE_BYTES, &maps.w[l][h][0], f0, c * KCH, row0);
+#ifdef DFW_DEBUG
+                            if (wp.dbg & 8) {        // dbg 8: no weight traffic at all (WRONG results): the barrier just completes
+                                if (leader) mbar_arrive(&bars->full[g]);
+                            } else
+#endif
+                            {
+                                if (leader) mbar_expect_tx(&bars->full[g], 2u * STAGE_BYTES);        // both CTAs' boxes
+                                tma_load_2d_2cta(sW + (size_t)rp.s * STAGE_BYTES, &maps.w[l][h][0], f0, c * KCH, row0);
+                            }
                         }
                         __syncwarp();
                     }
@@ -333,80 +513,102 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         // tcgen05.commit in the stream costs the pipe ~100-190 cycles.  Interleaving the next step's barrier probes between the MMA
         // groups made things worse (ptxas then spreads descriptor moves between the UTCHMMAs: 123 cycles per MMA), so the step
         // stays a plain block: probes, then the MMAs back to back inside ONE elect-guarded region, then the commits.
+        // It shares its scheduler with two epilogue and three gather warps and gets about a quarter of the issue slots while
+        // they run (measured: layer 1, under the FwFM interaction, took 26 k cycles against 14 k; with the gather warps of this
+        // scheduler idled, 16 k), so the loop is kept lean: explicit segment loops instead of index arithmetic, descriptors advanced
+        // by adds, ONE barrier probe and ONE slot-release commit per step when the ring is grouped (grp = 2).
         if (leader) {
             const uint32_t sW_u32 = smem_u32(sW), sX_u32 = smem_u32(sX);
+#ifdef DFW_DEBUG
+            const uint32_t idesc = make_idesc(256, (wp.dbg & 4) ? TSW : 2 * TSW) | (1u << 16);      // dbg 4: half-width MMAs (WRONG results)
+#else
             const uint32_t idesc = make_idesc(256, 2 * TSW) | (1u << 16);     // B is MN-major
+#endif
+            const uint64_t a_base = make_desc_sw128(sW_u32), b_base = make_desc_mn(sX_u32);
+            constexpr uint64_t A_SLOT = STAGE_BYTES >> 4, B_CH = (uint64_t)CH >> 4, B_LO = X_HBW >> 4;
+            const bool grouped = wp.grp == 2;
             RingPos rp{0, 0};
             uint32_t act_bits = 0;
             int gl = 0;                                                      // global layer counter: accumulator parity
             for (int it = 0; it < n_iter; ++it) {
                 for (int l = 0; l < L; ++l, ++gl) {
                     const int buf = gl & 1;
-                    const int K = layer_k(l), kch = (K + KCH - 1) / KCH, npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
-                    const int nstep = PT * kch, pt0_done = wide_pt0_done(PT, kch);
-                    const int x03_done = PT * (kch < 4 ? kch : 4) - 1;          // last step that reads chunks 0-3 of X
-                    for (int i = 0; i < nstep; ++i) {
-                        int pt, c;
-                        wide_step(i, PT, kch, pt, c);
-                        if (pt == 0) {
-                            if (l == 0) {
-                                if (c == 0) {
-                                    if (lane == 0 && it < 4) FZ_CLK(32 + 8 * it);
-                                    mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 21);
-                                    if (lane == 0 && it < 4) FZ_CLK(33 + 8 * it);
-                                }
-                            } else if ((c & 1) == 0) {
-                                const int g = c >> 1, bit = buf * MAX_MT + g;
-                                mbar_wait_cluster(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
-                                act_bits ^= 1u << bit;
-                            }
-                        }
-                        const int ks = min(4, (K - c * KCH) / 16);
+                    const int K = layer_k(l), kch = (K + KCH - 1) / KCH, PT = (n_mtiles(layer_n(l)) + 1) / 2;
+                    const int sp = kch < 4 ? kch : 4;
+                    const bool lastl = l == L - 1;
+#pragma unroll 1
+                    for (int seg = 0; seg < 4; ++seg) {
+                        const int pt = seg & 1;
+                        const int cb = seg < 2 ? 0 : sp, ce = seg < 2 ? sp : kch;
+                        if (pt >= PT || cb >= ce) continue;
                         const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + pt * 128);
-                        const uint64_t bhi = make_desc_mn(sX_u32 + (uint32_t)(c * CH));
-                        const uint64_t blo = make_desc_mn(sX_u32 + (uint32_t)(c * CH) + X_HBW);
-                        const uint32_t acc0 = c ? 1u : 0u;
-                        RingPos s0 = rp, s1 = rp;
-                        if (SPLIT) s1.next(NS);
-                        const bool k0 = mbar_try(&bars->full[s0.s], s0.ph), k1 = SPLIT ? mbar_try(&bars->full[s1.s], s1.ph) : true;
-                        if (!k0) mbar_wait_cluster(&bars->full[s0.s], s0.ph, p.err, 24);
-                        if (!k1) mbar_wait_cluster(&bars->full[s1.s], s1.ph, p.err, 25);
-                        tc_fence_after();
-                        const uint64_t ah = make_desc_sw128(sW_u32 + s0.s * (uint32_t)STAGE_BYTES);
-                        const uint64_t al = make_desc_sw128(sW_u32 + s1.s * (uint32_t)STAGE_BYTES);
-                        if (elect_one()) {
-                            umma_bf16_2cta(dcol, ah, bhi, idesc, acc0);
-                            if (ks > 1) umma_bf16_2cta(dcol, ah + 2, bhi + 16, idesc, 1u);
-                            if (ks > 2) umma_bf16_2cta(dcol, ah + 4, bhi + 32, idesc, 1u);
-                            if (ks > 3) umma_bf16_2cta(dcol, ah + 6, bhi + 48, idesc, 1u);
-                            if (SPLIT) {
-                                umma_bf16_2cta(dcol, ah, blo, idesc, 1u);                 // W_hi X_lo
-                                if (ks > 1) umma_bf16_2cta(dcol, ah + 2, blo + 16, idesc, 1u);
-                                if (ks > 2) umma_bf16_2cta(dcol, ah + 4, blo + 32, idesc, 1u);
-                                if (ks > 3) umma_bf16_2cta(dcol, ah + 6, blo + 48, idesc, 1u);
+#pragma unroll 1
+                        for (int c = cb; c < ce; ++c) {
+                            if (pt == 0) {
+                                if (l == 0) {
+                                    if (c == 0) {
+                                        if (lane == 0 && it < 4) FZ_CLK(32 + 8 * it);
+                                        mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 21);
+                                        if (lane == 0 && it < 4) FZ_CLK(33 + 8 * it);
+                                    }
+                                } else if ((c & 1) == 0) {
+                                    const int g = c >> 1, bit = buf * MAX_MT + g;
+                                    mbar_wait_cluster(&bars->act_ready[buf][g], (act_bits >> bit) & 1u, p.err, 22);
+                                    act_bits ^= 1u << bit;
+                                }
                             }
-                            umma_commit_2cta(&bars->empty[s0.s]);
-                            if (SPLIT) {
-                                umma_bf16_2cta(dcol, al, bhi, idesc, 1u);                 // W_lo X_hi
-                                if (ks > 1) umma_bf16_2cta(dcol, al + 2, bhi + 16, idesc, 1u);
-                                if (ks > 2) umma_bf16_2cta(dcol, al + 4, bhi + 32, idesc, 1u);
-                                if (ks > 3) umma_bf16_2cta(dcol, al + 6, bhi + 48, idesc, 1u);
-                                umma_commit_2cta(&bars->empty[s1.s]);
+                            const int ks = min(4, (K - c * KCH) / 16);
+                            const bool endc = c == kch - 1;
+                            RingPos s0 = rp, s1 = rp;
+                            if (SPLIT) s1.next(NS);
+                            const uint32_t g0 = grouped ? (s0.s >> 1) : s0.s, g1 = grouped ? (s1.s >> 1) : s1.s;
+                            // grouped + SPLIT: hi and lo box of the step share one barrier; grouped bf16: two steps share one
+                            const bool probe0 = !grouped || (s0.s & 1) == 0, probe1 = SPLIT && !grouped;
+                            const bool k0 = probe0 ? mbar_try(&bars->full[g0], s0.ph) : true;
+                            const bool k1 = probe1 ? mbar_try(&bars->full[g1], s1.ph) : true;
+                            if (!k0) mbar_wait_cluster(&bars->full[g0], s0.ph, p.err, 24);
+                            if (!k1) mbar_wait_cluster(&bars->full[g1], s1.ph, p.err, 25);
+                            tc_fence_after();
+                            const uint64_t ah = a_base + s0.s * A_SLOT, al = a_base + s1.s * A_SLOT;
+                            const uint64_t bhi = b_base + (uint64_t)c * B_CH, blo = bhi + B_LO;
+                            // pair-tile 0 may go to the epilogue once it is complete AND nothing reads chunks 0-3 any more
+                            const bool acc0_done = endc && (pt == 0 ? (kch > sp || PT == 1) : kch <= sp);
+                            if (elect_one()) {
+                                umma_bf16_2cta(dcol, ah, bhi, idesc, c ? 1u : 0u);
+                                if (ks > 1) umma_bf16_2cta(dcol, ah + 2, bhi + 16, idesc, 1u);
+                                if (ks > 2) umma_bf16_2cta(dcol, ah + 4, bhi + 32, idesc, 1u);
+                                if (ks > 3) umma_bf16_2cta(dcol, ah + 6, bhi + 48, idesc, 1u);
+                                if (SPLIT) {
+                                    umma_bf16_2cta(dcol, ah, blo, idesc, 1u);                 // W_hi X_lo
+                                    if (ks > 1) umma_bf16_2cta(dcol, ah + 2, blo + 16, idesc, 1u);
+                                    if (ks > 2) umma_bf16_2cta(dcol, ah + 4, blo + 32, idesc, 1u);
+                                    if (ks > 3) umma_bf16_2cta(dcol, ah + 6, blo + 48, idesc, 1u);
+                                    if (!grouped) umma_commit_2cta(&bars->empty[g0]);
+                                    umma_bf16_2cta(dcol, al, bhi, idesc, 1u);                 // W_lo X_hi
+                                    if (ks > 1) umma_bf16_2cta(dcol, al + 2, bhi + 16, idesc, 1u);
+                                    if (ks > 2) umma_bf16_2cta(dcol, al + 4, bhi + 32, idesc, 1u);
+                                    if (ks > 3) umma_bf16_2cta(dcol, al + 6, bhi + 48, idesc, 1u);
+                                    umma_commit_2cta(&bars->empty[g1]);
+                                } else if (!grouped || (s0.s & 1)) {
+                                    umma_commit_2cta(&bars->empty[g0]);
+                                }
+                                if (acc0_done) umma_commit_2cta(&bars->acc_full[buf][0]);
+                                if (pt == 1 && endc) umma_commit_2cta(&bars->acc_full[buf][1]);
+                                if (lastl && c == sp - 1 && pt == PT - 1) umma_commit_2cta(&bars->x_free03);
+                                if (lastl && endc && pt == PT - 1) umma_commit_2cta(&bars->x_free);
                             }
-                            if (i == pt0_done) umma_commit_2cta(&bars->acc_full[buf][0]);
-                            if (PT > 1 && i == nstep - 1) umma_commit_2cta(&bars->acc_full[buf][1]);
-                            if (l == L - 1 && i == x03_done) umma_commit_2cta(&bars->x_free03);
-                            if (l == L - 1 && i == nstep - 1) umma_commit_2cta(&bars->x_free);
+                            __syncwarp();
+                            rp = s1; rp.next(NS);
                         }
-                        __syncwarp();
-                        rp = s1; rp.next(NS);
                     }
                     if (lane == 0 && it < 4 && l < 4) FZ_CLK(34 + 8 * it + l);
                 }
             }
         }
+      } else {
+        gather_role();
       }
-    } else if (warp < W_G0) {
+    } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================================================================= epilogue: set h = the samples of CTA h
         const int h = (warp - W_EPI0) >> 2, q4 = warp & 3;
@@ -502,7 +704,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             if ((lane & 1) == 0) {
 #pragma unroll
                 for (int blk = 0; blk < 4; ++blk)
-                    st_cluster_f32(mapa_u32(smem_u32(&bars->red[par][rank][q4][16 * blk + (lane >> 1)]), (uint32_t)h), zsum[blk]);
+                    st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][q4][16 * blk + (lane >> 1)]), (uint32_t)h), zsum[blk]);
             }
             asm volatile("fence.acq_rel.cluster;" ::: "memory");
             tc_fence_before();
@@ -521,7 +723,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
 #pragma unroll
                     for (int r = 0; r < 2; ++r)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) z += bars->red[par][r][q][s];
+                        for (int q = 0; q < 4; ++q) z += bars->red[r][q][s];
                     if (b0 + s < p.B) {
                         if (p.logits) p.logits[b0 + s] = z;
                         if (p.prob) p.prob[b0 + s] = 1.0f / (1.0f + expf(-z));
@@ -529,113 +731,6 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 }
                 if (lane == 0 && it < 4) FZ_CLK(39 + 8 * it);
             }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        // ================================================================= gather group: one tile ahead of the tensor pipe
-        const int gtid = threadIdx.x - 32 * W_G0, gw = warp - W_G0;
-        constexpr int FK = FT * KT, Kp = (FK + 15) & ~15, SPW = 32 / KT;        // SPW samples per warp and round
-        const ImgLayout IL = img_layout(FT, KT);
-        unsigned char* sImg = base + p.oImg;
-        float* sPart = reinterpret_cast<float*>(base + p.oPart);
-        float* sNum = reinterpret_cast<float*>(base + wp.oNum);
-        const EmbedParams& ep = p.ep;
-        // model state once per CTA: shallow image (descriptors, fwlw weights) and the numeric fields' single rows
-        for (uint32_t i = gtid; i < (uint32_t)(IL.total >> 4); i += G_THREADS_W) cp_async16(sImg + 16 * i, ep.image + 16 * i);
-        cp_async_wait_all();
-        group_sync<BAR_G>(G_THREADS_W);
-        const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg + IL.oHdr);
-        const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + IL.oFields);
-        const float* sWl = reinterpret_cast<const float*>(sImg + IL.oWl);
-        const bool plain = hdr->any_special == 0;
-        for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
-            const int f = i / KT, k = i - f * KT;
-            sNum[i] = __ldg((plain ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
-        }
-        group_sync<BAR_G>(G_THREADS_W);
-
-        const int sl = lane / KT, kk = lane - sl * KT;
-        const int slot = gw * SPW + sl;                         // sample of each half-tile this thread owns (0..31), if any
-        const bool owner = sl < SPW && slot < 32;
-        const bool fwlw = ep.flags & DFW_USE_FWLW;
-        constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
-        bool joined = false;
-        for (int it = 0; it < n_iter; ++it) {
-            const int par = it & 1;
-            const long long q = cluster_id + (long long)it * n_clusters;
-            const int64_t b0 = (2 * q + rank) * TSW;
-            const int64_t ba = b0 + slot, bb = b0 + 32 + slot;
-            const bool livea = owner && ba < ep.B, liveb = owner && bb < ep.B;
-            // ---- rows of this thread's two samples (32 + slot, then slot) into registers: one copy of the load code, all of it under
-            //      the previous tile's MLP
-            float e0[FT], e1[FT];
-#pragma unroll 1
-            for (int r = 1; r >= 0; --r) {
-                if (plain) wide_load<FT, KT, NUMT, true>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, e0);
-                else wide_load<FT, KT, NUMT, false>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, e0);
-                if (r) {
-#pragma unroll
-                    for (int f = 0; f < FT; ++f) e1[f] = e0[f];
-                }
-            }
-            if (gtid == 0 && it < 4) FZ_CLK(96 + 8 * it);
-            if (!joined) {
-                asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
-                cluster_wait();                             // set-up of both CTAs complete: barriers may be used
-                joined = true;
-            }
-            // ---- the tensor pipe releases X in two steps: chunks 0-3 after segment 2 of the previous tile's last layer, the rest
-            //      after its last MMA
-            if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
-            if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
-            if (owner) {
-                wide_write<SPLIT, FT, KT, 0, FSPLIT>(sX, slot, kk, e0);
-                wide_write<SPLIT, FT, KT, 0, FSPLIT>(sX, 32 + slot, kk, e1);
-            }
-            if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
-            if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
-            if (owner) {
-                wide_write<SPLIT, FT, KT, FSPLIT, FT>(sX, slot, kk, e0);
-                wide_write<SPLIT, FT, KT, FSPLIT, FT>(sX, 32 + slot, kk, e1);
-            }
-            // K padding columns [F*K, Kp) of all 64 samples are zero
-            for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
-                const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
-                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (sp >> 3) * X_SBO + (col & 63) * 16 + (sp & 7) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
-                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(0.f);
-            }
-            fence_async_smem();                         // these stores are local
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
-            if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
-            // ---- first order + FwFM second order of both samples from the registers, under layer 1's MMAs (one copy of the code)
-#pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
-                if (owner) {
-                    const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(ep, sF, r ? bb : ba, r ? liveb : livea, kk);
-                    sPart[kk * TSW + 32 * r + slot] = wide_interact<FT, KT>(e0, up, sWl, kk, fwlw, first);
-                }
-                if (r == 0) {
-#pragma unroll
-                    for (int f = 0; f < FT; ++f) e0[f] = e1[f];
-                }
-            }
-            group_sync<BAR_G>(G_THREADS_W);
-            if (gtid < TSW) {
-                float tot = 0.f;
-#pragma unroll 1
-                for (int k = 0; k < KT; ++k) tot += sPart[k * TSW + gtid];
-                bars->shallow[par][gtid] = tot + __ldg(ep.bias);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->shallow_ready);
-            if (gtid == 0 && it < 4) FZ_CLK(99 + 8 * it);
-            group_sync<BAR_G>(G_THREADS_W);             // sPart is free for the next tile
-        }
-        if (!joined) {      // a pair without any tile still takes part in the set-up handshake
-            asm volatile("bar.sync %0, %1;" ::"n"(BAR_SETUP), "n"(THREADS) : "memory");
-            cluster_wait();
         }
     }
 
