@@ -103,13 +103,18 @@ __device__ __forceinline__ void group_sync(int nthreads) {
 // ------------------------------------------------------------------------------------------ gather helpers
 // Where the stored row of category `idx` of a field lives: quotient-remainder split
 // (model/QREmbeddingBag.py:157-158) and rank sharding (owner = row mod P, local row = row div P).
+// x / d for the divisors this path meets (QR collisions, rank counts): a shift when d is a power of two (c = 4, P = 2 / 4 / 8: the
+// common case), the ~20-instruction division otherwise; the branch is uniform per field
+__device__ __forceinline__ uint32_t div_small(uint32_t x, uint32_t d) {
+    return (d & (d - 1)) == 0 ? x >> (31 - __clz((int)d)) : x / d;
+}
 __device__ __forceinline__ const float* locate_row(const dfw_field_desc& fd, int32_t idx, int K) {
     uint32_t row = (uint32_t)idx;
-    if (fd.qr_op != DFW_TABLE_PLAIN) row = (uint32_t)idx / (uint32_t)fd.collisions;
+    if (fd.qr_op != DFW_TABLE_PLAIN) row = div_small((uint32_t)idx, (uint32_t)fd.collisions);
     const float* base = fd.w2;
     if (fd.n_ranks > 1) {
         const uint32_t P = (uint32_t)fd.n_ranks;
-        const uint32_t local = row / P;
+        const uint32_t local = div_small(row, P);
         base = fd.w2_shard[row - local * P];
         row = local;
     }

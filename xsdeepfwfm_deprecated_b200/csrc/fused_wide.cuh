@@ -163,7 +163,7 @@ __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field
                 const int op = fd.qr_op;
                 if (op != DFW_TABLE_PLAIN) {
                     const uint32_t cc = (uint32_t)fd.collisions;
-                    const float r = __ldg(fd.w2_r + (idx[c] - (idx[c] / cc) * cc) * KT + kk);
+                    const float r = __ldg(fd.w2_r + (idx[c] - div_small(idx[c], cc) * cc) * KT + kk);
                     e[NUMT + c] = op == DFW_TABLE_QR_MULT ? e[NUMT + c] * r : e[NUMT + c] + r;
                 }
             }

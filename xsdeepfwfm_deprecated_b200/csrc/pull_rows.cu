@@ -13,7 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "dfw_common.cuh"
+#include "embed_device.cuh"
 
 namespace dfw {
 namespace pl {
@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(THREADS, 16) pull_rows_kernel(const PullParams
                 idx = 0;
             }
             const uint32_t c = (uint32_t)fd.collisions;
-            const uint32_t q = (uint32_t)idx / c;            // stored row: the quotient for a QR table
+            const uint32_t q = div_small((uint32_t)idx, c);      // stored row: the quotient for a QR table
             const uint32_t P = (uint32_t)fd.n_ranks;
-            const uint32_t local = q / P;
+            const uint32_t local = div_small(q, P);
             const float* src = fd.w2_shard[q - local * P] + (size_t)local * p.K;
             float* dst = sbuf + t * p.K;
             for (uint32_t v = 0; v < nV; ++v) cp_async_f(dst + v * SEGW, src + v * SEGW, 4 * SEGW);
