@@ -90,7 +90,7 @@ def parse():
                     choices=["bf16x3", "bf16", "fp32", "fp32_csr"])
     ap.add_argument("--nbatches", type=int, default=256, help="distinct input batches cycled (> L2 in total)")
     ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=8,
                     help="concurrent streams the K independent forwards are spread over (1 = strictly back to back)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -337,8 +337,8 @@ def run_ours(args):
     # K steps as CUDA-graph replays of G-step segments (each segment walks distinct batches)
     graphs, tails, G = [], {}, 0
     if args.graph:
-        G = min(16, args.steps)
-        nseg = max(1, min(nb // G, 16))
+        G = min(64, args.steps)          # one graph holds every timed step when K <= 64 (no graph boundary drains the 4 streams)
+        nseg = max(1, min(nb // G, 16 if G <= 16 else 4))
         for s in range(nseg):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):

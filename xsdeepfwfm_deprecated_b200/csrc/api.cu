@@ -23,7 +23,17 @@ struct FwdLayout {
     size_t oErr, oImg, oE, oEb, oShallow, oMlp, total;
 };
 
+// bf16 on a shape neither the fused kernel nor the staged tensor MLP (F*K <= 512, widths <= 512) takes runs the CUDA-core fp32 MLP
+// (stricter, slower) -- the same fallback bf16x3 has
+static bool bf16_staged_ok(const dfw_model* m) {
+    if (m->field_size * m->embedding_size > 512) return false;
+    for (int l = 0; l < m->depth; ++l)
+        if (m->widths[l] > 512) return false;
+    return true;
+}
+
 static FwdLayout fwd_layout(const dfw_model* m, int64_t B, int precision) {
+    if (precision == DFW_PREC_BF16 && (m->flags & DFW_USE_DEEP) && !bf16_staged_ok(m)) precision = DFW_PREC_FP32;
     FwdLayout L;
     const int FK = m->field_size * m->embedding_size;
     L.ldE = (FK + 3) / 4 * 4;
@@ -129,6 +139,7 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
                            const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
                            void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
                            int32_t* err_word, void* stream) {
+    dfw::NvtxRange nvtx_("DeepFMs.forward (dfw_forward)");
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");
     if (B == 0) return 0;
@@ -141,6 +152,8 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     DFW_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, DFW_E_ARG, "workspace must be 256-byte aligned");
     char* ws = static_cast<char*>(workspace);
     const bool deep = m->flags & DFW_USE_DEEP;
+    const int requested = precision;          // what the fused kernel is asked for; the staged kernels may fall back to fp32
+    if (precision == DFW_PREC_BF16 && deep && !bf16_staged_ok(m)) precision = DFW_PREC_FP32;
     float* E = (deep && precision != DFW_PREC_BF16) ? reinterpret_cast<float*>(ws + L.oE) : nullptr;
     void* Eb = (deep && precision == DFW_PREC_BF16) ? static_cast<void*>(ws + L.oEb) : nullptr;
     float* shallow = reinterpret_cast<float*>(ws + L.oShallow);
@@ -154,8 +167,8 @@ extern "C" int dfw_forward(const dfw_model* m, const int64_t* xi, int64_t xi_str
     }
     // one kernel for the whole forward when the tensor-core form fits the model's shapes
     static const bool no_fused = dbg_getenv("DFW_NO_FUSED") != nullptr;
-    if (deep && !no_fused && (precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3) && dfw_fused_supported(m, precision))
-        return dfw_forward_fused(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, precision, logits_out,
+    if (deep && !no_fused && (requested == DFW_PREC_BF16 || requested == DFW_PREC_BF16X3) && dfw_fused_supported(m, requested))
+        return dfw_forward_fused(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, requested, logits_out,
                                  prob_out, err_word, stream);
     if (int rc = dfw_embed_fwfm(m, xi, xi_stride_b, xi_stride_c, xv, xv_stride_b, xv_stride_c, B, E, L.ldE, Eb, L.ldEb,
                                 shallow, err_word, stream))
@@ -318,6 +331,7 @@ extern "C" size_t dfw_forward_host_stream_workspace_bytes(const dfw_model* m, in
 extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_host, const float* xv_host, int64_t N,
                                        int64_t batch, int precision, void* workspace, size_t workspace_bytes,
                                        float* logits_host, float* prob_host, void* stream) {
+    dfw::NvtxRange nvtx_("eval_by_batch / predict_proba (dfw_forward_host_stream)");
     if (int rc = check_model(m)) return rc;
     if (N <= 0) return 0;
     DFW_REQUIRE(batch > 0, DFW_E_ARG, "batch must be positive");
@@ -366,11 +380,14 @@ extern "C" int dfw_forward_host_stream(const dfw_model* m, const int64_t* xi_hos
             bool lane_touched[kChunkSlots][kLanes] = {};
             for (int64_t k = 0; done < N; ++k) {
                 const int slot = (int)(k % nslots);
-                int g = k < 3 ? (1 << k) : chunk_cap;                      // 1, 2, 4, then full chunks
-                if (g > chunk_cap) g = chunk_cap;
                 const int64_t left = N - done;
-                int64_t nb = (left + batch - 1) / batch;
-                if (nb > g) nb = g;
+                const int64_t left_b = (left + batch - 1) / batch;
+                // chunk sizes ramp up 1, 2, 4, .. and taper off the same way (at most half of what is left): a short call pays a
+                // one-batch copy before its first kernel and a one-batch compute after its last copy, not a chunk's worth of either
+                int64_t g = k < 3 ? (1 << k) : chunk_cap;
+                if (g > chunk_cap) g = chunk_cap;
+                if (g > (left_b + 1) / 2) g = (left_b + 1) / 2;
+                int64_t nb = left_b < g ? left_b : g;
                 const int64_t rows = nb * batch < left ? nb * batch : left;
                 char* ws = static_cast<char*>(workspace) + (size_t)slot * slot_bytes;
                 char* xi_dev = ws;                                         // [nb x Xi][nb x Xv]: each batch's Xi / Xv contiguous

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <atomic>
+#include <nvtx3/nvToolsExt.h>
 
 #include "deepfwfm_b200.h"
 
@@ -70,6 +71,16 @@ inline int check_model(const dfw_model* m) {
 __device__ __forceinline__ float sigmoidf_dev(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range for the duration of a C-ABI call, named after the region of the reference's forward it replaces (the
+// torch.profiler.record_function names of model/DeepFMs.py:294-395), so that a timeline of this library lines up with one of the
+// reference.  nvtx3 is header-only and a no-op (one predictable branch) unless a tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Tuning / experiment knobs are read from the environment ONLY in a -DDFW_DEBUG build (python -m ...build --debug).  The
 // shipped library reads no environment variable at all, so nothing outside the caller's arguments can change what a timed

@@ -234,6 +234,7 @@ extern "C" int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_
                               const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B,
                               float* E_out, int64_t ldE, void* E_bf16_out, int64_t ldEb,
                               float* shallow_out, int32_t* err_word, void* stream) {
+    dfw::NvtxRange nvtx_("FM - Component: FM FW LW + FM Outer FwFM + FM Second Order (dfw_embed_fwfm)");
     using namespace dfw;
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(B >= 0, DFW_E_ARG, "negative batch");

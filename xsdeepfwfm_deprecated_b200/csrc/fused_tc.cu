@@ -934,6 +934,7 @@ extern "C" int dfw_pack_mlp_bf16_split(const float* W, int32_t out_dim, int32_t 
 extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t xi_stride_b, int64_t xi_stride_c,
                                  const float* xv, int64_t xv_stride_b, int64_t xv_stride_c, int64_t B, int precision,
                                  float* logits_out, float* prob_out, int32_t* err_word, void* stream) {
+    dfw::NvtxRange nvtx_("FM - Component + Deep - Component, one kernel (dfw_forward_fused)");
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(precision == DFW_PREC_BF16 || precision == DFW_PREC_BF16X3, DFW_E_ARG,
                 "the fused kernel computes in bf16 or bf16x3, not precision %d", precision);

@@ -166,6 +166,7 @@ extern "C" size_t dfw_mlp_workspace_bytes(const dfw_model* m, int64_t B, int pre
 extern "C" int dfw_mlp_fp32(const dfw_model* m, const float* X, int64_t ldX, int64_t B, const float* shallow,
                             void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out,
                             void* stream) {
+    dfw::NvtxRange nvtx_("Deep - Component (dfw_mlp_fp32)");
     using namespace dfw;
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(m->flags & DFW_USE_DEEP, DFW_E_ARG, "model has no deep part");

@@ -155,6 +155,7 @@ extern "C" int dfw_csr_fill(const float* W, int32_t out_dim, int32_t in_dim, con
 
 extern "C" int dfw_mlp_csr(const dfw_model* m, const float* X, int64_t ldX, int64_t B, const float* shallow,
                            void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out, void* stream) {
+    dfw::NvtxRange nvtx_("Deep - Component, CSR (dfw_mlp_csr)");
     (void)workspace; (void)workspace_bytes;
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(m->flags & DFW_USE_DEEP, DFW_E_ARG, "model has no deep part");

@@ -345,6 +345,7 @@ extern "C" int dfw_pack_mlp_bf16(const float* W, int32_t out_dim, int32_t in_dim
 
 extern "C" int dfw_mlp_bf16(const dfw_model* m, const void* Xb, int64_t ldXb, int64_t B, const float* shallow,
                             void* workspace, size_t workspace_bytes, float* logits_out, float* prob_out, void* stream) {
+    dfw::NvtxRange nvtx_("Deep - Component, tcgen05 (dfw_mlp_bf16)");
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(m->flags & DFW_USE_DEEP, DFW_E_ARG, "model has no deep part");
     DFW_REQUIRE(Xb && (logits_out || prob_out), DFW_E_ARG, "X / outputs NULL");

@@ -104,6 +104,7 @@ using namespace dfw;
 extern "C" int dfw_pull_rows(const dfw_model* m, const int32_t* sharded_fields, int32_t n_sharded, const int64_t* xi,
                              int64_t xi_stride_b, int64_t xi_stride_c, int64_t B, float* staged_out, void* xi2_out,
                              int32_t* err_word, void* stream) {
+    dfw::NvtxRange nvtx_("sharded row exchange (dfw_pull_rows)");
     if (int rc = check_model(m)) return rc;
     DFW_REQUIRE(B >= 0 && B < (1ll << 24), DFW_E_ARG, "batch %lld outside [0, 2^24)", (long long)B);
     if (B == 0) return 0;

@@ -146,7 +146,7 @@ class _Plan:
         self.model = m
         self.model_ref = C.byref(m)
         self.params = params
-        self.ptrs = tuple(p.data_ptr() for p in params)
+        self.ptrs = tuple((p.data_ptr(), p._version) for p in params)
         # shallow image: U / pair list / fwlw weights / descriptors in the kernel's shared-memory layout
         nimg = lib.dfw_shallow_image_bytes(self.model_ref)
         self.shallow_image = torch.zeros(nimg, dtype=torch.uint8, device=dev)
@@ -162,7 +162,10 @@ class _Plan:
         self.host_ws = None
 
     def stale(self) -> bool:
-        return self.ptrs != tuple(p.data_ptr() for p in self.params)
+        """Re-bound storage (init_weights, .cuda()) or an in-place edit that autograd's version counter sees (copy_, mul_, an
+        optimizer step).  Edits through ``param.data[...] = ...`` (the reference's pruner) bypass that counter: tables and fp32
+        MLP weights are read in place anyway, the derived images (shallow image, bf16 / CSR weights) need eval() / repack()."""
+        return self.ptrs != tuple((p.data_ptr(), p._version) for p in self.params)
 
     # -- derived images ------------------------------------------------------------------
     def ensure_image(self, owner: "DeepFMs", precision: str):
@@ -425,6 +428,7 @@ class DeepFMs(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self._plan = None
+        self._host_ws = None
         return super()._apply(fn, *a, **kw)
 
     def train(self, mode: bool = True):
@@ -455,6 +459,10 @@ class DeepFMs(nn.Module):
 
         Returns logits (B,) fp32 -- the reference's ``total_sum`` (model/DeepFMs.py:458-469).  With
         ``return_prob=True`` also returns sigmoid(logits), fused into the last kernel.
+
+        Streams: the fused single-kernel path (``bf16x3`` / ``bf16`` on the dataset shapes) uses no workspace, so forwards of one
+        module may overlap on several streams.  The staged paths (``fp32``, ``fp32_csr``, shapes outside the fused kernel)
+        keep E and the activations in ONE per-module workspace: run those on one stream at a time.
         """
         if self.training and self.use_deep and self.is_deep_dropout:
             raise RuntimeError("this implementation is inference-only: call .eval() first (train-mode dropout "
@@ -536,14 +544,18 @@ class DeepFMs(nn.Module):
         Xv_np = np.asarray(Xv_np).reshape(n, -1)
         bs = min(batch_size, max(n, 1))
         chunk = bs * max(1, min(batches_in_flight, -(-max(n, 1) // bs)))
-        if plan.host_ws is None or plan.host_ws[0] != bs or plan.host_ws[1] != prec or plan.host_ws[2] < chunk:
+        # the pinned staging buffers and the device workspace belong to the module, not to the plan: eval() (which every
+        # inference entry point of the reference calls first) drops the plan, and re-pinning four buffers per call costs milliseconds
+        hw = getattr(self, "_host_ws", None)
+        if hw is None or hw[0] != (bs, prec, str(dev), self.index_dtype) or hw[2] < chunk:
             nbytes = lib.dfw_forward_host_stream_workspace_bytes(plan.model_ref, bs, prec)
-            plan.host_ws = (bs, prec, chunk, torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev),
+            self._host_ws = ((bs, prec, str(dev), self.index_dtype), None, chunk,
+                             torch.zeros(nbytes + 4096, dtype=torch.uint8, device=dev),
                             torch.empty(chunk * C_, dtype=t_idx).pin_memory(),
                             torch.empty(chunk * max(self.num, 1), dtype=torch.float32).pin_memory(),
                             torch.empty(chunk, dtype=torch.float32).pin_memory(),
                             torch.empty(chunk, dtype=torch.float32).pin_memory())
-        _, _, chunk, ws, pxi, pxv, pprob, plogit = plan.host_ws
+        _, _, chunk, ws, pxi, pxv, pprob, plogit = self._host_ws
         out = np.empty(n, dtype=np.float32)
         out_logit = np.empty(n, dtype=np.float32) if want_logits else None
         st = _stream_ptr(dev)
@@ -707,6 +719,7 @@ class DeepFMs(nn.Module):
     def __getstate__(self):
         d = self.__dict__.copy()
         d['_plan'] = None
+        d.pop('_host_ws', None)
         if 'logger' in d:
             d['logger'] = d['logger'].name
         return d
