@@ -36,6 +36,7 @@ import torch  # noqa: E402
 METRIC = "DeepFwFM inference samples/sec"
 UNIT = "samples/s"
 K_EMB, NODES, DEPTH = 10, 400, 3
+SHARD_ROWS = int(os.environ.get("DFW_BENCH_SHARD_ROWS", "65536"))
 FIELD = NUM = CATS = 0
 SIZES, MODEL_KW, WORKLOAD_TEXT, XV_UNIT, PRUNED = None, {}, "", False, False
 ALG_BYTES_PER_SAMPLE = ALG_BYTES_PER_BATCH = MLP_FLOPS_PER_SAMPLE = 0
@@ -157,7 +158,9 @@ def make_model(device, precision, feature_sizes, world=1, exchange=None, index_d
               index_dtype=index_dtype, **MODEL_KW)
     if world > 1:
         from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
-        m = ShardedDeepFMs(FIELD, feature_sizes, exchange=exchange, shard_threshold=200, **kw)
+        # shard what is large: tables above 65,536 rows (2.6 MB at K = 10) -- 6 of the 26 paper-Criteo tables = 89 % of the table bytes,
+        # 16 of the 36 Twitter tables = 99.9 %; a 12 k-row table is replicated (480 KB) rather than fetched over NVLink per sample
+        m = ShardedDeepFMs(FIELD, feature_sizes, exchange=exchange, shard_threshold=SHARD_ROWS, **kw)
     else:
         m = DeepFMs(FIELD, feature_sizes, **kw)
     m = m.to(device)
@@ -614,7 +617,7 @@ def run_ours(args):
                                  (f", the independent forwards round-robin over {nstreams} concurrent streams" if nstreams > 1
                                   else ", strictly back to back on one stream"),
                        "tables": "one GPU" if world == 1 else
-                                 f"{len(model._shards)} of {CATS} categorical tables row-sharded over {world} GPUs (row i on rank i mod P); " + ("rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"
+                                 f"{len(model._shards)} of {CATS} categorical tables (those above {SHARD_ROWS} rows) row-sharded over {world} GPUs (row i on rank i mod P), the rest replicated; " + ("rows fetched by direct peer loads over NVLink inside the fused gather kernel (no collective)"
                                     if not pull else "rows fetched by direct peer loads over NVLink (no collective) by a pull kernel "
                                     "that runs ahead of the fused kernel into a local staging buffer (exchange='p2p_pull')")},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,

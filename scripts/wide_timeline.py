@@ -14,7 +14,11 @@ lib = _lib.load()
 dev = torch.device("cuda", 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
-bench.set_workload(sys.argv[3] if len(sys.argv) > 3 else "criteo")
+wl = sys.argv[3] if len(sys.argv) > 3 else "criteo"
+bench.set_workload(wl.replace("_small", ""))
+if wl.endswith("_small"):          # the same switches on the paper-Criteo cardinalities (L2-resident tables)
+    from xsdeepfwfm_deprecated_b200.utils import workloads
+    bench.SIZES = workloads.CRITEO_PAPER
 m = bench.make_model(dev, prec, bench.SIZES)
 plan = m._get_plan(); plan.ensure_image(m, prec)
 Xi, Xv = bench.make_batches(dev, bench.SIZES, B, 4, seed=0)
@@ -46,7 +50,8 @@ for it in range(4):
     if not (c[lead, 33 + 8 * it] != 0).any():
         break
     print(f"-- tile {it}")
-    rows = [("gather: rows of both samples in registers", 96 + 8 * it, used), ("gather: chunks 0-3 of X released", 100 + 8 * it, used),
+    rows = [("gather: model state in shared memory (tile 0)", 102, used), ("gather: rows of the first sample in registers", 101 + 8 * it, used),
+            ("gather: rows of both samples in registers", 96 + 8 * it, used), ("gather: chunks 0-3 of X released", 100 + 8 * it, used),
             ("gather: X released (x_free)", 97 + 8 * it, used),
             ("gather: x_ready arrive", 98 + 8 * it, used), ("MMA: waits for x_ready", 32 + 8 * it, lead), ("MMA: x_ready seen", 33 + 8 * it, lead)]
     for l in range(L):

@@ -136,10 +136,19 @@ __device__ __forceinline__ void wide_idx(const EmbedParams& ep, int64_t b, bool 
     }
 }
 
-template <int FT, int KT, int NUMT, bool PLAIN>
+// How the categorical rows of a model are addressed -- decided once per CTA from the field descriptors, so that the per-sample
+// path carries no per-field case analysis (the generic form costs ~40 instructions per field and sample: 20 k cycles per pass):
+//   GM_PLAIN    every table plain and local: row = w2 + idx * K
+//   GM_SHARD    plain tables, some row-sharded over a power-of-two rank count: owner = idx & (P - 1), local row = idx >> log2 P
+//   GM_QR       quotient-remainder tables with a power-of-two collision count, nothing sharded: q = idx >> log2 c, r = idx & (c - 1)
+//   GM_GENERIC  anything else (QR and sharding together, other divisors)
+enum { GM_PLAIN = 0, GM_SHARD = 1, GM_QR = 2, GM_GENERIC = 3 };
+
+template <int FT, int KT, int NUMT, int MODE>
 __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field_desc* sF, const float* sNum, int64_t b,
                                           bool live, int kk, uint32_t (&idx)[FT - NUMT > 0 ? FT - NUMT : 1], float (&e)[FT]) {
     constexpr int CT = FT - NUMT;
+    constexpr bool PLAIN = MODE == GM_PLAIN;
     if (live) {
         if (ep.err) {       // DFW_CHECK_INDEX: the full 64-bit value must be inside the table
 #pragma unroll 1
@@ -148,23 +157,59 @@ __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field
                 if (v < 0 || v >= sF[NUMT + c].rows) atomicExch(ep.err, 1 + NUMT + c);
             }
         }
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            const dfw_field_desc& fd = sF[NUMT + c];
-            if (idx[c] >= (uint32_t)fd.rows) idx[c] = 0;          // defined behaviour instead of a wild read
-            const float* src = PLAIN ? fd.w2 + (size_t)idx[c] * KT : locate_row(fd, (int32_t)idx[c], KT);
-            e[NUMT + c] = __ldg(src + kk);
-        }
-        if constexpr (!PLAIN) {
-            // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172); the c-row remainder tables are L1-resident
+        if constexpr (MODE == GM_QR) {
+            // branch-free: every field issues both loads (a plain table of a QR model reads its own row twice and ignores the second),
+            // so all 2 x 26 loads are in flight together; with a branch per field ptxas kept each load next to its use and a pass
+            // took 26 dependent L2 round trips (20 k cycles)
+            float r[CT > 0 ? CT : 1];
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
                 const dfw_field_desc& fd = sF[NUMT + c];
-                const int op = fd.qr_op;
-                if (op != DFW_TABLE_PLAIN) {
-                    const uint32_t cc = (uint32_t)fd.collisions;
-                    const float r = __ldg(fd.w2_r + (idx[c] - div_small(idx[c], cc) * cc) * KT + kk);
-                    e[NUMT + c] = op == DFW_TABLE_QR_MULT ? e[NUMT + c] * r : e[NUMT + c] + r;
+                uint32_t i = idx[c];
+                if (i >= (uint32_t)fd.rows) i = 0;                // defined behaviour instead of a wild read
+                const bool isqr = fd.qr_op != DFW_TABLE_PLAIN;
+                const uint32_t cc = isqr ? (uint32_t)fd.collisions : 1u;          // a plain table of a QR model: q = i, no remainder
+                const uint32_t q = i >> (31 - __clz((int)cc));
+                const float* qrow = fd.w2 + (size_t)q * KT + kk;
+                const float* rrow = isqr ? fd.w2_r + (i & (cc - 1)) * KT + kk : qrow;
+                e[NUMT + c] = __ldg(qrow);
+                r[c] = __ldg(rrow);
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {      // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172)
+                const int op = sF[NUMT + c].qr_op;
+                const float v = e[NUMT + c];
+                e[NUMT + c] = op == DFW_TABLE_QR_MULT ? v * r[c] : op == DFW_TABLE_QR_ADD ? v + r[c] : v;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const dfw_field_desc& fd = sF[NUMT + c];
+                if (idx[c] >= (uint32_t)fd.rows) idx[c] = 0;          // defined behaviour instead of a wild read
+                const float* src;
+                if constexpr (MODE == GM_PLAIN) {
+                    src = fd.w2 + (size_t)idx[c] * KT;
+                } else if constexpr (MODE == GM_SHARD) {
+                    // branch-free: a replicated table is "sharded over one rank" whose pointer is w2
+                    const uint32_t P = fd.n_ranks > 1 ? (uint32_t)fd.n_ranks : 1u;
+                    const float* const* tbl = fd.n_ranks > 1 ? fd.w2_shard : &fd.w2;
+                    src = tbl[idx[c] & (P - 1)] + (size_t)(idx[c] >> (31 - __clz((int)P))) * KT;
+                } else {
+                    src = locate_row(fd, (int32_t)idx[c], KT);
+                }
+                e[NUMT + c] = __ldg(src + kk);
+            }
+            if constexpr (MODE == GM_GENERIC) {
+                // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172); the c-row remainder tables are L1-resident
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    const dfw_field_desc& fd = sF[NUMT + c];
+                    const int op = fd.qr_op;
+                    if (op != DFW_TABLE_PLAIN) {
+                        const uint32_t cc = (uint32_t)fd.collisions;
+                        const float r = __ldg(fd.w2_r + (idx[c] - div_small(idx[c], cc) * cc) * KT + kk);
+                        e[NUMT + c] = op == DFW_TABLE_QR_MULT ? e[NUMT + c] * r : e[NUMT + c] + r;
+                    }
                 }
             }
         }
@@ -173,7 +218,7 @@ __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field
 #pragma unroll
         for (int f = 0; f < NUMT; ++f) {
             float v = sNum[f * KT + kk];
-            if constexpr (!PLAIN) {
+            if constexpr (!PLAIN && MODE != GM_SHARD) {
                 const int op = sF[f].qr_op;
                 if (op == DFW_TABLE_QR_MULT) v *= __ldg(sF[f].w2_r + kk);
                 else if (op == DFW_TABLE_QR_ADD) v += __ldg(sF[f].w2_r + kk);
@@ -279,7 +324,9 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
     constexpr int H = SPLIT ? 2 : 1;
     constexpr int CH = H * (int)X_HBW;                  // one K chunk of the activation buffer: hi [| lo] of 64 samples
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (128-byte swizzle atoms) as an OFFSET into the shared array: rounding the pointer itself through uintptr_t
+    // loses the address space, and every access through `base` then compiles to generic LD.E / ST.E instead of LDS / STS
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sX = base;
     unsigned char* sW = base + p.oRing;
     WideBars* bars = reinterpret_cast<WideBars*>(base + p.oMisc);
@@ -369,7 +416,8 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         const int sa = 2 * slot;                                // tile-local samples sa, sa + 1
         const bool fwlw = ep.flags & DFW_USE_FWLW;
         constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
-        bool joined = false, plain = true;
+        bool joined = false;
+        int gmode = GM_PLAIN;
         for (int it = 0; it < n_iter; ++it) {
             const int par = it & 1;
             const long long q = cluster_id + (long long)it * n_clusters;
@@ -387,18 +435,34 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 if (it == 0 && r == 1) {
                     cp_async_wait_all();
                     group_sync<BAR_G>(G_THREADS_W);                 // header, fwlw weights, descriptors are in shared memory
-                    plain = hdr->any_special == 0;
+                    gmode = GM_PLAIN;
+                    if (hdr->any_special) {
+                        bool qr = false, sh = false, odd = false;
+                        for (int f = 0; f < FT; ++f) {
+                            const dfw_field_desc& fd = sF[f];
+                            const uint32_t cc = (uint32_t)fd.collisions, P = (uint32_t)fd.n_ranks;
+                            if (fd.qr_op != DFW_TABLE_PLAIN) { qr = true; odd |= f < NUMT || cc == 0 || (cc & (cc - 1)) != 0; }
+                            if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
+                        }
+                        gmode = (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
+                    }
                     for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
                         const int f = i / KT, k = i - f * KT;
-                        sNum[i] = __ldg((plain ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
+                        sNum[i] = __ldg((gmode == GM_PLAIN ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
                     }
                     group_sync<BAR_G>(G_THREADS_W);
+                    if (gtid == 0) FZ_CLK(102);
                 }
-                if (plain) wide_rows<FT, KT, NUMT, true>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, ix, e0);
-                else wide_rows<FT, KT, NUMT, false>(ep, sF, sNum, r ? bb : ba, r ? liveb : livea, kk, ix, e0);
+                const int64_t bl = r ? bb : ba;
+                const bool lv = r ? liveb : livea;
+                if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(ep, sF, sNum, bl, lv, kk, ix, e0);
+                else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(ep, sF, sNum, bl, lv, kk, ix, e0);
+                else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(ep, sF, sNum, bl, lv, kk, ix, e0);
+                else wide_rows<FT, KT, NUMT, GM_GENERIC>(ep, sF, sNum, bl, lv, kk, ix, e0);
                 if (r) {
 #pragma unroll
                     for (int f = 0; f < FT; ++f) e1[f] = e0[f];
+                    if (gtid == 0 && it < 4) FZ_CLK(101 + 8 * it);
                 }
             }
             if (gtid == 0 && it < 4) FZ_CLK(96 + 8 * it);
