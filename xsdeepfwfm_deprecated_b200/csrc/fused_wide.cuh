@@ -445,6 +445,10 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                             if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
                         }
                         gmode = (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
+#ifdef DFW_DEBUG
+                        if (wp.dbg & 32) gmode = GM_GENERIC;          // timing experiments: force the generic addressing form
+                        if (gtid == 0 && blockIdx.x == 0 && (wp.dbg & 64)) printf("gmode %d qr %d sh %d odd %d\n", gmode, (int)qr, (int)sh, (int)odd);
+#endif
                     }
                     for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
                         const int f = i / KT, k = i - f * KT;
