@@ -28,6 +28,7 @@
 //
 // Bytes per sample the algorithm needs (Criteo, fwlw): 26*8 + 13*4 + 26*40 + 4 = 1304.
 #include "embed_device.cuh"
+#include "fused_wide.cuh"
 
 namespace dfw {
 
@@ -192,6 +193,91 @@ embed_fwfm_kernel(const EmbedParams p) {
     embed_interact<FT, KT, kS, 1, 0>(p, sm, tid, nthreads, nrows, first_acc, p.shallow + b0, clk);
 }
 
+// ------------------------------------------------------------------------------------------ register-gather kernel
+// The shallow part only (no E output: FM / FwFM models without the deep part, BASELINE config 1) for the dataset shapes, with the
+// gather of the fused kernel (fused_wide.cuh): a thread owns one embedding column of one sample, ten lanes cover a 40-byte row,
+// three rows per warp instruction -- every row load of a sample is in flight at once, whole sectors, no shared-memory block, no
+// cp.async pieces, no fix-up pass -- and the first + second order run from the registers with the field matrix as constant-bank
+// operands.  Persistent grid-stride loop; 2 CTAs x 8 warps per SM keep ~13 k row loads in flight per SM.  HBM-bound: 1304
+// algorithmic bytes per sample (two 32-byte sectors per 40-byte row: 0.68 of peak is the ceiling of the algorithmic fraction).
+constexpr int RG_WARPS = 8, RG_THREADS = 32 * RG_WARPS;
+
+template <int FT, int KT, int NUMT>
+__global__ void __launch_bounds__(RG_THREADS, 2) embed_reg_kernel(const __grid_constant__ fz::UParam up, const EmbedParams p) {
+    using namespace fz::wd;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const ImgLayout IL = img_layout(FT, KT);
+    constexpr uint32_t W_WL = 16, W_FIELDS = W_WL + (uint32_t)up16(sizeof(float) * FT * KT);
+    constexpr uint32_t W_NUM = W_FIELDS + (uint32_t)up16(sizeof(dfw_field_desc) * FT);
+    unsigned char* sImg = smem_raw;
+    float* sNum = reinterpret_cast<float*>(smem_raw + W_NUM);
+    if (tid == 0) cp_async16(sImg, p.image + IL.oHdr);
+    for (uint32_t i = tid; i < (uint32_t)(up16(sizeof(float) * FT * KT) >> 4); i += RG_THREADS) cp_async16(sImg + W_WL + 16 * i, p.image + IL.oWl + 16 * i);
+    for (uint32_t i = tid; i < (uint32_t)(up16(sizeof(dfw_field_desc) * FT) >> 4); i += RG_THREADS) cp_async16(sImg + W_FIELDS + 16 * i, p.image + IL.oFields + 16 * i);
+    cp_async_wait_all();
+    __syncthreads();
+    const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg);
+    const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + W_FIELDS);
+    const float* sWl = reinterpret_cast<const float*>(sImg + W_WL);
+    int gmode = GM_PLAIN;
+    if (hdr->any_special) {
+        bool qr = false, sh = false, odd = false;
+        for (int f = 0; f < FT; ++f) {
+            const dfw_field_desc& fd = sF[f];
+            const uint32_t cc = (uint32_t)fd.collisions, P = (uint32_t)fd.n_ranks;
+            if (fd.qr_op != DFW_TABLE_PLAIN) { qr = true; odd |= f < NUMT || cc == 0 || (cc & (cc - 1)) != 0; }
+            if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
+        }
+        gmode = (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
+    }
+    for (int i = tid; i < NUMT * KT; i += RG_THREADS) {
+        const int f = i / KT, k = i - f * KT;
+        sNum[i] = __ldg((gmode == GM_PLAIN ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
+    }
+    __syncthreads();
+    constexpr int CT = FT - NUMT > 0 ? FT - NUMT : 1, SPW = 32 / KT, PER_CTA = RG_WARPS * SPW;
+    const int sl = lane / KT, kk = lane - sl * KT;
+    const bool fwlw = p.flags & DFW_USE_FWLW;
+    const float bias = __ldg(p.bias);
+    for (int64_t base = (int64_t)blockIdx.x * PER_CTA; base < p.B; base += (int64_t)gridDim.x * PER_CTA) {
+        const int64_t b = base + warp * SPW + sl;
+        const bool live = sl < SPW && b < p.B;
+        float e[FT];
+        uint32_t ix[CT];
+        wide_idx<CT>(p, b, live, ix);
+        if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(p, sF, sNum, b, live, kk, ix, e);
+        else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(p, sF, sNum, b, live, kk, ix, e);
+        else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(p, sF, sNum, b, live, kk, ix, e);
+        else wide_rows<FT, KT, NUMT, GM_GENERIC>(p, sF, sNum, b, live, kk, ix, e);
+        float v = 0.f;
+        if (live) {
+            const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(p, sF, b, live, kk);
+            v = wide_interact<FT, KT>(e, up, sWl, kk, fwlw, first);
+        }
+        // fixed-order sum over the sample's K lanes (the order of embed_interact's phase E), + bias
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) tot += __shfl_sync(0xffffffffu, v, (sl < SPW ? sl : 0) * KT + k);
+        if (live && kk == 0) p.shallow[b] = tot + bias;
+    }
+}
+
+template <int FT, int KT, int NUMT>
+static int launch_embed_reg(const fz::UParam& up, const EmbedParams& p, cudaStream_t st) {
+    auto kern = embed_reg_kernel<FT, KT, NUMT>;
+    const size_t smem = 16 + up16(sizeof(float) * FT * KT) + up16(sizeof(dfw_field_desc) * FT) + up16(sizeof(float) * (NUMT > 0 ? NUMT : 1) * KT);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    constexpr int PER_CTA = RG_WARPS * (32 / KT);
+    const long long want = (p.B + PER_CTA - 1) / PER_CTA;
+    const unsigned grid = (unsigned)(want < 2LL * sms ? want : 2LL * sms);
+    kern<<<grid, RG_THREADS, smem, st>>>(up, p);
+    count_launch();
+    return check_launch("embed_reg_kernel");
+}
+
 template <int FT, int KT>
 static int launch_embed(const EmbedParams& p, cudaStream_t st) {
     const SmemLayout L = smem_layout(p.F, p.K, p.num);
@@ -255,6 +341,15 @@ extern "C" int dfw_embed_fwfm(const dfw_model* m, const int64_t* xi, int64_t xi_
     p.shallow = shallow_out; p.err = (m->flags & DFW_CHECK_INDEX) ? err_word : nullptr;
     p.B = B; p.F = F; p.num = num; p.K = K; p.flags = m->flags; p.clk = g_clk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // shallow part only, dataset shapes, field matrix available as a kernel parameter: the register-gather kernel
+    if (!E_out && !E_bf16_out && K == 10 && ((F == 39 && num == 13) || (F == 47 && num == 11))) {
+        static thread_local fz::UParam up;
+        fz::build_uparam(m, up);
+        if (up.valid) {
+            if (F == 39) return launch_embed_reg<39, 10, 13>(up, p, st);
+            return launch_embed_reg<47, 10, 11>(up, p, st);
+        }
+    }
     // the two dataset shapes BASELINE.json names get the fully unrolled dense second order
     if (F == 39 && K == 10) return launch_embed<39, 10>(p, st);
     if (F == 47 && K == 10) return launch_embed<47, 10>(p, st);

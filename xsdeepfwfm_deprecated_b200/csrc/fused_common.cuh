@@ -79,6 +79,25 @@ __host__ __device__ inline int mtile_rows(int npad, int mt) {
 constexpr int MAX_U = 1168;                    // usize(47) + 4 = 1156 floats (usize(39) = 800)
 struct alignas(16) UParam { int valid; int pad_[3]; float u[MAX_U]; };
 
+// U = strict upper triangle of (R + R^T) / 2 by columns, in fp32 exactly as pack_shallow_kernel computes it (valid = 1), or ones
+// for FM (model/DeepFMs.py:353-355; valid = 2).  valid = 0: no host snapshot of field_cov, or F too large for the parameter.
+inline void build_uparam(const dfw_model* m, UParam& up) {
+    const int F = m->field_size;
+    up.valid = 0;
+    if (usize(F) + 4 > MAX_U) return;
+    if ((m->flags & DFW_USE_FWFM) && m->field_cov_host) {
+        const float* cov = m->field_cov_host;
+        for (int j = 1; j < F; ++j)
+            for (int i = 0; i < pad4(j); ++i)
+                up.u[ucol_off(j) + i] = i < j ? (cov[j * F + i] + cov[i * F + j]) * 0.5f : 0.f;
+        up.valid = 1;
+    } else if (!(m->flags & DFW_USE_FWFM)) {
+        for (int j = 1; j < F; ++j)
+            for (int i = 0; i < pad4(j); ++i) up.u[ucol_off(j) + i] = i < j ? 1.f : 0.f;
+        up.valid = 2;
+    }
+}
+
 struct RingPos {
     uint32_t s, ph;
     __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1; } }

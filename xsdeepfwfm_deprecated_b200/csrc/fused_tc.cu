@@ -963,20 +963,7 @@ extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t 
     p.fc = m->fc; p.logits = logits_out; p.prob = prob_out; p.B = B;
     p.num_tiles = (int)((B + fz::TS - 1) / fz::TS);
     p.err = err_word; p.clk = fz::g_clk; p.prog = fz::g_prog;
-    // U = strict upper triangle of (R + R^T) / 2 by columns, in fp32 exactly as pack_shallow_kernel computes it
-    pl.up.valid = 0;
-    if ((m->flags & DFW_USE_FWFM) && m->field_cov_host && usize(F) + 4 <= fz::MAX_U) {
-        const float* cov = m->field_cov_host;
-        for (int j = 1; j < F; ++j)
-            for (int i = 0; i < pad4(j); ++i)
-                pl.up.u[ucol_off(j) + i] = i < j ? (cov[j * F + i] + cov[i * F + j]) * 0.5f : 0.f;
-        pl.up.valid = 1;
-    } else if (!(m->flags & DFW_USE_FWFM) && usize(F) + 4 <= fz::MAX_U) {
-        // FM (model/DeepFMs.py:353-355): every pair weighs 1; valid = 2 marks "ones" for the kernels that walk the pair list otherwise
-        for (int j = 1; j < F; ++j)
-            for (int i = 0; i < pad4(j); ++i) pl.up.u[ucol_off(j) + i] = i < j ? 1.f : 0.f;
-        pl.up.valid = 2;
-    }
+    fz::build_uparam(m, pl.up);
     fz::Maps maps;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // the two dataset shapes BASELINE.json names get the fully unrolled dense second order
