@@ -91,7 +91,7 @@ def parse():
                     choices=["bf16x3", "bf16", "fp32", "fp32_csr"])
     ap.add_argument("--nbatches", type=int, default=256, help="distinct input batches cycled (> L2 in total)")
     ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=8,
+    ap.add_argument("--streams", type=int, default=16,
                     help="concurrent streams the K independent forwards are spread over (1 = strictly back to back)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -155,7 +155,7 @@ def make_model(device, precision, feature_sizes, world=1, exchange=None, index_d
     from xsdeepfwfm_deprecated_b200.model import DeepFMs
     kw = dict(embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False, use_fwfm=True, use_deep=True,
               use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision,
-              index_dtype=index_dtype, **MODEL_KW)
+              index_dtype=index_dtype, throughput_hint=True, **MODEL_KW)
     if world > 1:
         from xsdeepfwfm_deprecated_b200.sharded import ShardedDeepFMs
         # shard what is large: tables above 65,536 rows (2.6 MB at K = 10) -- 6 of the 26 paper-Criteo tables = 89 % of the table bytes,

@@ -59,6 +59,11 @@ extern "C" {
                                     host batch sends over PCIe.  Strides stay in elements; the `const int64_t*` parameters are then
                                     plain addresses of int32 data */
 
+#define DFW_HINT_THROUGHPUT (1u << 10) /* several forwards of this model are kept in flight (a serving loop, bench.py's streams): the
+                                    fused kernel then gives each CTA pair two tiles, so that the second tile's gather runs under the
+                                    first one's MLP -- 16 % less SM time per batch, 60 % more latency of a launch that runs alone.
+                                    Results are bit-identical either way. */
+
 /* qr_op of a table (model/QREmbeddingBag.py:167-172) */
 #define DFW_TABLE_PLAIN 0
 #define DFW_TABLE_QR_MULT 1

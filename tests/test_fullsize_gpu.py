@@ -129,3 +129,25 @@ def test_config2_bf16_full_size_bound_and_auc():
     assert np.abs(got - ref["logit"]).max() <= logit_tol(ref["logit"], BF16_REL)
     y = (np.random.default_rng(4).random(4096) < ref["prob"]).astype(np.int64)
     assert abs(roc_auc_score(y, got) - roc_auc_score(y, ref["logit"])) <= BF16_AUC
+
+
+def test_throughput_hint_is_bit_identical_and_survives_concurrent_host_streaming():
+    """DFW_HINT_THROUGHPUT gives every CTA pair of the fused kernel two tiles.  (1) Same bits as without the hint.  (2) The
+    scenario that exposed a barrier hazard in round 2 (a 1-bit parity wait overrun by the gather group while the finisher was
+    delayed): many multi-tile launches in flight on several streams, storing their results to pinned host memory while the copy
+    engine streams inputs in -- 40 calls x 64 batches of 4096 through dfw_forward_host_stream, bit-identical to forward()."""
+    cfg = PathConfig(39, synth.CRITEO_PAPER, use_fm=False, use_fwfm=True, use_deep=True, use_fwlw=True)
+    w = synth.make_weights(cfg, seed=42)
+    Xi, Xv = synth.make_inputs(cfg, 64 * 4096, seed=12)
+    plain = to_cuda(cfg, w, precision="bf16x3")
+    hinted = to_cuda(cfg, w, precision="bf16x3", throughput_hint=True)
+    txi, txv = torch.from_numpy(Xi).cuda(), torch.from_numpy(Xv).cuda()
+    with torch.no_grad():
+        a = torch.cat([plain(txi[i:i + 4096], txv[i:i + 4096]) for i in range(0, len(Xi), 4096)])
+        b = torch.cat([hinted(txi[i:i + 4096], txv[i:i + 4096]) for i in range(0, len(Xi), 4096)])
+        big = hinted(txi, txv)                                  # one launch, 14 tiles per pair
+    assert torch.equal(a, b) and torch.equal(a, big)
+    want = torch.sigmoid(a).cpu().numpy()
+    for rep in range(40):
+        got = hinted.predict_proba_host(Xi, Xv, batch_size=4096, batches_in_flight=64)
+        assert np.array_equal(got, want), rep

@@ -18,6 +18,7 @@ DFW_MAX_K = 32
 DFW_MAX_RANKS = 8
 
 USE_FWFM, USE_FWLW, USE_LW, USE_DEEP, CHECK_INDEX, XI_INT32 = 1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 8, 1 << 9
+HINT_THROUGHPUT = 1 << 10
 TABLE_PLAIN, TABLE_QR_MULT, TABLE_QR_ADD = 0, 1, 2
 PREC_FP32, PREC_BF16, PREC_FP32_CSR, PREC_BF16X3 = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32_csr": PREC_FP32_CSR, "bf16x3": PREC_BF16X3}

@@ -593,6 +593,7 @@ __global__ void pack_split_kernel(const float* __restrict__ W, int out_dim, int 
 // ---------------------------------------------------------------------------------------- host side
 static long long* g_clk = nullptr;
 static volatile int* g_prog = nullptr;
+static int* g_errword = nullptr;          // debug: where a barrier watchdog writes its code when the caller passes no error word
 
 struct Plan {
     Params p;
@@ -862,6 +863,17 @@ static int launch_wide(const dfw_model* m, const Plan& pl, Maps& maps, cudaStrea
         if (cap > 0 && cap < pairs) pairs = cap;
     }
     if (wp.n_pair_tiles < pairs) pairs = wp.n_pair_tiles;
+    {
+        // Tiles per pair.  A pair that owns ONE tile pays the whole gather (20 k cycles) in front of its first MMA: 68 k cycles per
+        // tile; from the second tile on the gather runs under the previous tile's MLP: (20 + 2 x 43 + 3.5 + 5) / 2 = 57 k per tile.
+        // With DFW_HINT_THROUGHPUT (several launches in flight) a launch that has the tiles for it therefore uses half as many pairs
+        // with two tiles each: 16 % less SM time per batch (measured 204 -> 238 M samples/s at B = 4096 with 16 launches in
+        // flight; three tiles per pair gain nothing more), 67 instead of 41 us for a launch running alone -- hence a hint.
+        static const int tpp_env = env_int("DFW_WIDE_TPP", 0);
+        const int tpp = tpp_env > 0 ? tpp_env : ((m->flags & DFW_HINT_THROUGHPUT) && wp.n_pair_tiles >= 8) ? 2 : 1;
+        const int want = (wp.n_pair_tiles + tpp - 1) / tpp;
+        if (want < pairs) pairs = want;
+    }
     kern<<<(unsigned)(2 * pairs), wd::THREADS, smem_bytes, st>>>(maps, pl.up, wp);
     count_launch();
     return check_launch("fused_wide_kernel");
@@ -913,6 +925,8 @@ using namespace dfw;
 extern "C" void dfw_debug_set_fused_clock_buffer(void* dev_buf) { fz::g_clk = static_cast<long long*>(dev_buf); }
 // Debug tooling: progress markers (32 ints per CTA) written to pinned host memory, readable after a watchdog trap.
 extern "C" void dfw_debug_set_fused_progress_buffer(void* host_buf) { fz::g_prog = static_cast<volatile int*>(host_buf); }
+// Debug tooling: a (pinned host) word that receives the code of a timed-out barrier wait when the caller gave no error word.
+extern "C" void dfw_debug_set_fused_error_word(void* host_word) { fz::g_errword = static_cast<int*>(host_word); }
 
 extern "C" int dfw_fused_supported(const dfw_model* m, int precision) {
     if (check_model(m)) return 0;
@@ -962,7 +976,7 @@ extern "C" int dfw_forward_fused(const dfw_model* m, const int64_t* xi, int64_t 
     for (int l = 0; l < m->depth; ++l) { p.widths[l] = m->widths[l]; p.bias[l] = m->b[l]; }
     p.fc = m->fc; p.logits = logits_out; p.prob = prob_out; p.B = B;
     p.num_tiles = (int)((B + fz::TS - 1) / fz::TS);
-    p.err = err_word; p.clk = fz::g_clk; p.prog = fz::g_prog;
+    p.err = err_word ? err_word : fz::g_errword; p.clk = fz::g_clk; p.prog = fz::g_prog;
     fz::build_uparam(m, pl.up);
     fz::Maps maps;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

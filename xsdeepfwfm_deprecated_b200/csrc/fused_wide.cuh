@@ -54,7 +54,10 @@ struct WideBars {
     uint64_t x_ready;                // leader: layer-1 operand of the tile written in both CTAs (2 x W_G arrives)
     uint64_t x_free;                 // per CTA: every MMA of the tile has completed, X may be overwritten (multicast commit)
     uint64_t x_free03;               // per CTA: chunks 0-3 of X are dead already (after segment 2 of the tile's last layer)
-    uint64_t shallow_ready;          // per CTA: W_G arrives per tile
+    uint64_t shallow_ready[2];       // per CTA, [tile parity]: W_G arrives per tile.  Two barriers because its waiter (the finisher) is not
+                                     // in the gather's dependency chain: with one, the gather could complete the NEXT tile's phase before a
+                                     // delayed finisher tested this tile's, and a 1-bit parity wait then never returns (seen as a hang of
+                                     // concurrent multi-tile launches that store to host memory)
     uint64_t act_ready[2][MAX_MT];   // leader: [layer parity][neuron tile], W_EPI arrives from the CTA that owns the tile
     uint64_t acc_full[2][2];         // per CTA: [layer parity][pair-tile] accumulators complete (multicast commit)
     uint64_t fin;                    // per CTA: the partial sums of its samples are in `red` (2 x 4 arrives per tile)
@@ -348,7 +351,8 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         mbar_init(&bars->x_ready, 2 * W_G);
         mbar_init(&bars->x_free, 1);
         mbar_init(&bars->x_free03, 1);
-        mbar_init(&bars->shallow_ready, W_G);
+        mbar_init(&bars->shallow_ready[0], W_G);
+        mbar_init(&bars->shallow_ready[1], W_G);
         mbar_init(&bars->fin, 2 * 4);
         for (int b = 0; b < 2; ++b) {
             for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], W_EPI);
@@ -519,7 +523,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 bars->shallow[par][gtid] = tot + __ldg(ep.bias);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->shallow_ready);
+            if (lane == 0) mbar_arrive(&bars->shallow_ready[par]);
             if (gtid == 0 && it < 4) FZ_CLK(99 + 8 * it);
             group_sync<BAR_G>(G_THREADS_W);             // sPart is free for the next tile
         }
@@ -781,7 +785,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
             if (warp == W_EPI0) {
                 // this CTA's samples of the tile: shallow part + the partial sums of both CTAs' neuron tiles
                 mbar_wait_cluster(&bars->fin, (uint32_t)par, p.err, 34);
-                mbar_wait(&bars->shallow_ready, (uint32_t)par, p.err, 33);
+                mbar_wait(&bars->shallow_ready[par], (uint32_t)((it >> 1) & 1), p.err, 33);
                 const long long ptile = cluster_id + (long long)it * n_clusters;
                 const long long b0 = (2 * ptile + rank) * TSW;
 #pragma unroll

@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
         if ((spin & 0x3ffu) == 0x3ffu && watchdog_expired(t0)) {     // only a broken pipeline gets here
-            if (err) atomicExch(err, code);
+            if (err) { atomicExch(err, code); atomicOr(err + 1, 1 << (code & 31)); }      // err[1]: set of waits that timed out (debug word)
             __trap();
         }
     }

@@ -127,6 +127,8 @@ class _Plan:
             flags |= _lib.CHECK_INDEX
         if getattr(owner, "index_dtype", "int64") == "int32":
             flags |= _lib.XI_INT32
+        if getattr(owner, "throughput_hint", False):
+            flags |= _lib.HINT_THROUGHPUT
         m.field_size, m.numerical, m.embedding_size = F, num, K
         m.fields = self.fields_dev.data_ptr()
         m.bias = chk(owner.bias, "bias").data_ptr()
@@ -228,7 +230,7 @@ class DeepFMs(nn.Module):
                  use_logit=0, embedding_bag=False, quantization_aware=False, dynamic_quantization=False,
                  static_quantization=False, static_calibrate=False,
                  qr_flag=0, qr_operation="mult", qr_collisions=1, qr_threshold=200, md_flag=0, md_threshold=200,
-                 logger=None, precision="fp32", check_index=False, index_dtype="int64"):
+                 logger=None, precision="fp32", check_index=False, index_dtype="int64", throughput_hint=False):
         super().__init__()
         self.field_size = field_size
         self.feature_sizes = feature_sizes
@@ -284,6 +286,10 @@ class DeepFMs(nn.Module):
         if index_dtype not in ("int64", "int32"):
             raise ValueError("index_dtype must be 'int64' or 'int32'")
         self.index_dtype = index_dtype
+        # True: several forwards of this module are kept in flight (serving loop, several streams): the fused kernel trades the
+        # latency of a lone launch for SM time per batch (DFW_HINT_THROUGHPUT); results are bit-identical.  Call repack() after
+        # changing it.
+        self.throughput_hint = bool(throughput_hint)
         self._plan: Optional[_Plan] = None
         self._frozen = False
 
