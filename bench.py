@@ -148,10 +148,11 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- workload
 def make_model(device, precision, feature_sizes, world=1, exchange=None, index_dtype="int64", keep_weights=None):
-    # exchange: "p2p_pull" (default) = peer rows fetched over NVLink by a small register-only kernel that runs one batch ahead of,
-    # and on the same SMs as, the fused kernel (two launches per step); "p2p" = the same loads inside the fused kernel's gather
-    # (one launch; the 64 resident CTAs cannot keep enough peer requests in flight: 35.6 vs 32.4 us/step at 2 GPUs)
-    exchange = exchange or os.environ.get("DFW_BENCH_EXCHANGE", "p2p_pull")
+    # exchange: "p2p" (default) = peer rows fetched over NVLink by the fused kernel's own gather (one launch per step; with two tiles
+    # per CTA pair the peer round trips of the second tile run under the first tile's MLP: 26.1 us/step at 2 and at 8 GPUs);
+    # "p2p_pull" = the same loads by a separate kernel one batch ahead into a local staging buffer (two launches; its CTAs cannot
+    # share an SM with the fused kernel's: 31.2 us/step)
+    exchange = exchange or os.environ.get("DFW_BENCH_EXCHANGE", "p2p")
     from xsdeepfwfm_deprecated_b200.model import DeepFMs
     kw = dict(embedding_size=K_EMB, h_depth=DEPTH, deep_nodes=NODES, use_fm=False, use_fwfm=True, use_deep=True,
               use_fwlw=True, use_lw=False, use_cuda=True, numerical=NUM, random_seed=42, precision=precision,

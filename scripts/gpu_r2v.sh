@@ -1,0 +1,7 @@
+N=${1:-2}
+mkdir -p gpurun_out/r2v
+for tpp in 2 3 4; do for w in criteo twitter; do
+DFW_WIDE_TPP=$tpp DFW_BENCH_EXCHANGE=p2p timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29562 bench.py --gpus $N --steps 20 --warmup 5 --workload $w --no-cpu-baseline > gpurun_out/r2v/bench_${w}_${N}gpu_tpp$tpp.json 2> gpurun_out/r2v/bench_${w}_${N}gpu_tpp$tpp.err; python -c "
+import json
+d=json.loads(open('gpurun_out/r2v/bench_${w}_${N}gpu_tpp$tpp.json').read().strip().splitlines()[-1]); print('BENCH tpp $tpp $w $N gpus', round(d['value']/1e6,1), d['ms_per_step'], 'e2e', round(d['e2e']['value']/1e6,1), {k:v['ms'] for k,v in d['roofline']['stages'].items()})"
+done; done

@@ -220,17 +220,8 @@ __global__ void __launch_bounds__(RG_THREADS, 2) embed_reg_kernel(const __grid_c
     const ImgHeader* hdr = reinterpret_cast<const ImgHeader*>(sImg);
     const dfw_field_desc* sF = reinterpret_cast<const dfw_field_desc*>(sImg + W_FIELDS);
     const float* sWl = reinterpret_cast<const float*>(sImg + W_WL);
-    int gmode = GM_PLAIN;
-    if (hdr->any_special) {
-        bool qr = false, sh = false, odd = false;
-        for (int f = 0; f < FT; ++f) {
-            const dfw_field_desc& fd = sF[f];
-            const uint32_t cc = (uint32_t)fd.collisions, P = (uint32_t)fd.n_ranks;
-            if (fd.qr_op != DFW_TABLE_PLAIN) { qr = true; odd |= f < NUMT || cc == 0 || (cc & (cc - 1)) != 0; }
-            if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
-        }
-        gmode = (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
-    }
+    int gmode = GM_PLAIN, qop = DFW_TABLE_PLAIN;
+    if (hdr->any_special) gmode = wide_gmode<FT, NUMT>(sF, qop);
     for (int i = tid; i < NUMT * KT; i += RG_THREADS) {
         const int f = i / KT, k = i - f * KT;
         sNum[i] = __ldg((gmode == GM_PLAIN ? sF[f].w2 : locate_row(sF[f], 0, KT)) + k);
@@ -246,10 +237,10 @@ __global__ void __launch_bounds__(RG_THREADS, 2) embed_reg_kernel(const __grid_c
         float e[FT];
         uint32_t ix[CT];
         wide_idx<CT>(p, b, live, ix);
-        if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(p, sF, sNum, b, live, kk, ix, e);
-        else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(p, sF, sNum, b, live, kk, ix, e);
-        else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(p, sF, sNum, b, live, kk, ix, e);
-        else wide_rows<FT, KT, NUMT, GM_GENERIC>(p, sF, sNum, b, live, kk, ix, e);
+        if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(p, sF, sNum, b, live, kk, qop, ix, e);
+        else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(p, sF, sNum, b, live, kk, qop, ix, e);
+        else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(p, sF, sNum, b, live, kk, qop, ix, e);
+        else wide_rows<FT, KT, NUMT, GM_GENERIC>(p, sF, sNum, b, live, kk, qop, ix, e);
         float v = 0.f;
         if (live) {
             const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(p, sF, b, live, kk);

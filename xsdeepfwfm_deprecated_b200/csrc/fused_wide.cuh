@@ -139,6 +139,21 @@ __device__ __forceinline__ void wide_idx(const EmbedParams& ep, int64_t b, bool 
     }
 }
 
+// Read-only loads with an L1 policy.  The 227 KB of shared memory leave the SM ~28 KB of L1: table rows stream through it without
+// allocating, so that the few hundred bytes every sample re-reads (QR remainder tables: c rows per field) stay resident -- without
+// this all 148 SMs fetch the same few L2 lines 26 times per sample and queue on those L2 banks (a QR pass took 8 k cycles
+// against 2 k for plain tables).
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_keep(const float* p) {
+    float v;
+    asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // How the categorical rows of a model are addressed -- decided once per CTA from the field descriptors, so that the per-sample
 // path carries no per-field case analysis (the generic form costs ~40 instructions per field and sample: 20 k cycles per pass):
 //   GM_PLAIN    every table plain and local: row = w2 + idx * K
@@ -147,9 +162,26 @@ __device__ __forceinline__ void wide_idx(const EmbedParams& ep, int64_t b, bool 
 //   GM_GENERIC  anything else (QR and sharding together, other divisors)
 enum { GM_PLAIN = 0, GM_SHARD = 1, GM_QR = 2, GM_GENERIC = 3 };
 
+// addressing mode of a model with special tables (QR / sharded), and THE quotient-remainder operation of a GM_QR model
+template <int FT, int NUMT>
+__device__ __forceinline__ int wide_gmode(const dfw_field_desc* sF, int& qop) {
+    bool qr = false, sh = false, odd = false;
+    qop = DFW_TABLE_PLAIN;
+    for (int f = 0; f < FT; ++f) {
+        const dfw_field_desc& fd = sF[f];
+        const uint32_t cc = (uint32_t)fd.collisions, P = (uint32_t)fd.n_ranks;
+        if (fd.qr_op != DFW_TABLE_PLAIN) {
+            odd |= f < NUMT || cc == 0 || (cc & (cc - 1)) != 0 || (qr && fd.qr_op != qop);
+            qr = true; qop = fd.qr_op;
+        }
+        if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
+    }
+    return (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
+}
+
 template <int FT, int KT, int NUMT, int MODE>
 __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field_desc* sF, const float* sNum, int64_t b,
-                                          bool live, int kk, uint32_t (&idx)[FT - NUMT > 0 ? FT - NUMT : 1], float (&e)[FT]) {
+                                          bool live, int kk, int qop, uint32_t (&idx)[FT - NUMT > 0 ? FT - NUMT : 1], float (&e)[FT]) {
     constexpr int CT = FT - NUMT;
     constexpr bool PLAIN = MODE == GM_PLAIN;
     if (live) {
@@ -161,28 +193,31 @@ __device__ __forceinline__ void wide_rows(const EmbedParams& ep, const dfw_field
             }
         }
         if constexpr (MODE == GM_QR) {
-            // branch-free: every field issues both loads (a plain table of a QR model reads its own row twice and ignores the second),
-            // so all 2 x 26 loads are in flight together; with a branch per field ptxas kept each load next to its use and a pass
-            // took 26 dependent L2 round trips (20 k cycles)
-            float r[CT > 0 ? CT : 1];
+            // One operation for the whole model (the reference has a single qr_operation: model/DeepFMs.py:96-108), so the combine
+            // is a select, not a branch per field; a plain table of a QR model combines with the neutral element (x * 1, x + 0:
+            // exact).  Two halves of 13 fields: quotient + remainder loads of all 26 fields at once are 52 results on top of the other
+            // sample's 26 rows -- ptxas spilled the remainders and the operation codes, and the combine then ran as 40 dependent
+            // local-memory loads (a pass took 15 k cycles against 2 k for plain tables).
+            const float neutral = qop == DFW_TABLE_QR_MULT ? 1.f : 0.f;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {
-                const dfw_field_desc& fd = sF[NUMT + c];
-                uint32_t i = idx[c];
-                if (i >= (uint32_t)fd.rows) i = 0;                // defined behaviour instead of a wild read
-                const bool isqr = fd.qr_op != DFW_TABLE_PLAIN;
-                const uint32_t cc = isqr ? (uint32_t)fd.collisions : 1u;          // a plain table of a QR model: q = i, no remainder
-                const uint32_t q = i >> (31 - __clz((int)cc));
-                const float* qrow = fd.w2 + (size_t)q * KT + kk;
-                const float* rrow = isqr ? fd.w2_r + (i & (cc - 1)) * KT + kk : qrow;
-                e[NUMT + c] = __ldg(qrow);
-                r[c] = __ldg(rrow);
-            }
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = h ? CT / 2 : 0, c1 = h ? CT : CT / 2;
+                float r[(CT + 1) / 2 > 0 ? (CT + 1) / 2 : 1];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) {      // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172)
-                const int op = sF[NUMT + c].qr_op;
-                const float v = e[NUMT + c];
-                e[NUMT + c] = op == DFW_TABLE_QR_MULT ? v * r[c] : op == DFW_TABLE_QR_ADD ? v + r[c] : v;
+                for (int c = c0; c < c1; ++c) {
+                    const dfw_field_desc& fd = sF[NUMT + c];
+                    uint32_t i = idx[c];
+                    if (i >= (uint32_t)fd.rows) i = 0;                // defined behaviour instead of a wild read
+                    const bool isqr = fd.qr_op != DFW_TABLE_PLAIN;
+                    const uint32_t cc = isqr ? (uint32_t)fd.collisions : 1u;          // a plain table of a QR model: q = i, no remainder
+                    const uint32_t q = i >> (31 - __clz((int)cc));
+                    e[NUMT + c] = ldg_stream(fd.w2 + (size_t)q * KT + kk);
+                    r[c - c0] = neutral;
+                    if (isqr) r[c - c0] = ldg_keep(fd.w2_r + (i & (cc - 1)) * KT + kk);
+                }
+#pragma unroll
+                for (int c = c0; c < c1; ++c)      // quotient row (x|+) remainder row (model/QREmbeddingBag.py:169-172)
+                    e[NUMT + c] = qop == DFW_TABLE_QR_MULT ? e[NUMT + c] * r[c - c0] : e[NUMT + c] + r[c - c0];
             }
         } else {
 #pragma unroll
@@ -421,7 +456,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         const bool fwlw = ep.flags & DFW_USE_FWLW;
         constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
         bool joined = false;
-        int gmode = GM_PLAIN;
+        int gmode = GM_PLAIN, qop = DFW_TABLE_PLAIN;           // qop: THE operation of a QR model (GM_QR needs a single one)
         for (int it = 0; it < n_iter; ++it) {
             const int par = it & 1;
             const long long q = cluster_id + (long long)it * n_clusters;
@@ -441,17 +476,10 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     group_sync<BAR_G>(G_THREADS_W);                 // header, fwlw weights, descriptors are in shared memory
                     gmode = GM_PLAIN;
                     if (hdr->any_special) {
-                        bool qr = false, sh = false, odd = false;
-                        for (int f = 0; f < FT; ++f) {
-                            const dfw_field_desc& fd = sF[f];
-                            const uint32_t cc = (uint32_t)fd.collisions, P = (uint32_t)fd.n_ranks;
-                            if (fd.qr_op != DFW_TABLE_PLAIN) { qr = true; odd |= f < NUMT || cc == 0 || (cc & (cc - 1)) != 0; }
-                            if (P > 1) { sh = true; odd |= (P & (P - 1)) != 0; }
-                        }
-                        gmode = (odd || (qr && sh)) ? GM_GENERIC : qr ? GM_QR : sh ? GM_SHARD : GM_PLAIN;
+                        gmode = wide_gmode<FT, NUMT>(sF, qop);
 #ifdef DFW_DEBUG
                         if (wp.dbg & 32) gmode = GM_GENERIC;          // timing experiments: force the generic addressing form
-                        if (gtid == 0 && blockIdx.x == 0 && (wp.dbg & 64)) printf("gmode %d qr %d sh %d odd %d\n", gmode, (int)qr, (int)sh, (int)odd);
+                        if (gtid == 0 && blockIdx.x == 0 && (wp.dbg & 64)) printf("gmode %d qop %d\n", gmode, qop);
 #endif
                     }
                     for (int i = gtid; i < NUMT * KT; i += G_THREADS_W) {
@@ -463,10 +491,10 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 }
                 const int64_t bl = r ? bb : ba;
                 const bool lv = r ? liveb : livea;
-                if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(ep, sF, sNum, bl, lv, kk, ix, e0);
-                else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(ep, sF, sNum, bl, lv, kk, ix, e0);
-                else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(ep, sF, sNum, bl, lv, kk, ix, e0);
-                else wide_rows<FT, KT, NUMT, GM_GENERIC>(ep, sF, sNum, bl, lv, kk, ix, e0);
+                if (gmode == GM_PLAIN) wide_rows<FT, KT, NUMT, GM_PLAIN>(ep, sF, sNum, bl, lv, kk, qop, ix, e0);
+                else if (gmode == GM_SHARD) wide_rows<FT, KT, NUMT, GM_SHARD>(ep, sF, sNum, bl, lv, kk, qop, ix, e0);
+                else if (gmode == GM_QR) wide_rows<FT, KT, NUMT, GM_QR>(ep, sF, sNum, bl, lv, kk, qop, ix, e0);
+                else wide_rows<FT, KT, NUMT, GM_GENERIC>(ep, sF, sNum, bl, lv, kk, qop, ix, e0);
                 if (r) {
 #pragma unroll
                     for (int f = 0; f < FT; ++f) e1[f] = e0[f];
