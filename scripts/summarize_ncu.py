@@ -52,7 +52,7 @@ def full(rep, out):
             f.write("\n")
 
 
-for prec in ("fp32", "bf16", "bf16x3"):
+for prec in ("fp32", "bf16", "bf16x3", "b65536_bf16x3", "b65536_bf16"):
     p = os.path.join(src, f"launches_{prec}.csv")
     if os.path.exists(p):
         launches(p, os.path.join(dst, f"{tag}_launches_{prec}.csv"))
