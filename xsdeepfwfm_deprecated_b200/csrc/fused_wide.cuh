@@ -507,28 +507,39 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 cluster_wait();                             // set-up of both CTAs complete: barriers may be used
                 joined = true;
             }
-            // ---- the tensor pipe releases X in two steps: chunks 0-3 after segment 2 of the previous tile's last layer, the rest
-            //      after its last MMA
-            if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
-            if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
-            if (owner) wide_write2<SPLIT, FT, KT, 0, FSPLIT>(sX, sa, kk, e0, e1);
-            if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
-            if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
-            if (owner) wide_write2<SPLIT, FT, KT, FSPLIT, FT>(sX, sa, kk, e0, e1);
-            // K padding columns [F*K, Kp) of all 64 samples are zero
-            for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
-                const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
-                unsigned char* dst = sX + (size_t)(col >> 6) * CH + (sp >> 3) * X_SBO + (col & 63) * 16 + (sp & 7) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
-                if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(0.f);
-            }
-            fence_async_smem();                         // these stores are local
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
-            if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
-            // ---- first order + FwFM second order of both samples from the registers, under layer 1's MMAs (one copy of the code)
+            // ---- first order + FwFM second order of both samples from the registers (ONE copy of the code), and in between the
+            //      operand write.  From the second tile on sample a's interaction runs FIRST, in the time the gather group would
+            //      otherwise wait for the tensor pipe to release X (rows are in registers ~8 k cycles before x_free03): only sample
+            //      b's half is then left to run under layer 1, and it ends before layer 1's epilogue starts (next to the
+            //      interaction that epilogue took 6.2 + 5.0 k cycles per pair-tile instead of 5.0 + 3.0 k).  The first tile of a
+            //      launch has nothing to hide under and writes first.
 #pragma unroll 1
             for (int r = 0; r < 2; ++r) {
+                if (r == (it == 0 ? 0 : 1)) {
+                    // the tensor pipe releases X in two steps: chunks 0-3 after segment 2 of the previous tile's last layer, the
+                    // rest after its last MMA
+                    if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
+                    if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
+                    if (owner) wide_write2<SPLIT, FT, KT, 0, FSPLIT>(sX, sa, kk, e0, e1);
+                    if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
+                    if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
+                    if (owner) wide_write2<SPLIT, FT, KT, FSPLIT, FT>(sX, sa, kk, e0, e1);
+                    // K padding columns [F*K, Kp) of all 64 samples are zero
+                    for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
+                        const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
+                        unsigned char* dst = sX + (size_t)(col >> 6) * CH + (sp >> 3) * X_SBO + (col & 63) * 16 + (sp & 7) * 2;
+                        *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(0.f);
+                        if constexpr (SPLIT) *reinterpret_cast<__nv_bfloat16*>(dst + X_HBW) = __float2bfloat16_rn(0.f);
+                    }
+                    fence_async_smem();                         // these stores are local
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
+                    if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
+                }
+                if (r == 1) {
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) e0[f] = e1[f];
+                }
 #ifdef DFW_DEBUG
                 const bool dbg_skip = (wp.dbg & 2) || ((wp.dbg & 1) && (warp & 3) == 1);       // WRONG logits: timeline experiments only
 #else
@@ -537,10 +548,6 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                 if (owner && !dbg_skip) {
                     const float first = fwlw ? 0.f : wide_first<FT, KT, NUMT>(ep, sF, r ? bb : ba, r ? liveb : livea, kk);
                     sPart[kk * TSW + sa + r] = wide_interact<FT, KT>(e0, up, sWl, kk, fwlw, first);
-                }
-                if (r == 0) {
-#pragma unroll
-                    for (int f = 0; f < FT; ++f) e0[f] = e1[f];
                 }
             }
             group_sync<BAR_G>(G_THREADS_W);
