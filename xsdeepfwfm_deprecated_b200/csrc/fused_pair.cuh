@@ -55,6 +55,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive on a barrier of another CTA of the cluster with CTA-scope release (the form CUTLASS's ClusterBarrier::arrive(cta_id) uses).
+// For a hand-off to the ASYNC proxy (tcgen05.mma operands): the writer's fence.proxy.async has already waited for its stores --
+// measured: it returns ~130 cycles after local stores and only after 1.3-1.8 k cycles when 8 KB of st.shared::cluster are still
+// draining -- so the cluster-scope release of mbar_arrive_cluster (MEMBAR.ALL.GPU + ERRBAR: 0.8-1.9 k cycles per arrive even with
+// nothing outstanding) adds latency to the hand-off and no ordering the consumer needs.
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void st_cluster_b16(uint32_t cluster_addr, __nv_bfloat16 v) {
     asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(cluster_addr), "h"(*reinterpret_cast<const uint16_t*>(&v)) : "memory");
 }

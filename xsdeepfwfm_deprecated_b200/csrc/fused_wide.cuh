@@ -533,7 +533,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     }
                     fence_async_smem();                         // these stores are local
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->x_ready), 0));
+                    if (lane == 0) mbar_arrive_remote_cta(mapa_u32(smem_u32(&bars->x_ready), 0));
                     if (gtid == 0 && it < 4) FZ_CLK(98 + 8 * it);
                 }
                 if (r == 1) {
@@ -802,7 +802,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                         else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->act_ready[(gl + 1) & 1][t]), 0));
+                        if (lane == 0) mbar_arrive_remote_cta(mapa_u32(smem_u32(&bars->act_ready[(gl + 1) & 1][t]), 0));
                     }
                     if (threadIdx.x == 32 * W_EPI0 && it < 2 && l < 4) FZ_CLK(65 + 16 * it + 4 * l + 2 * j);
                 }
