@@ -388,7 +388,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         mbar_init(&bars->x_free03, 1);
         mbar_init(&bars->shallow_ready[0], W_G);
         mbar_init(&bars->shallow_ready[1], W_G);
-        mbar_init(&bars->fin, 2 * 4);
+        mbar_init(&bars->fin, 2 * W_EPI);          // every epilogue warp of the pair holds partial sums of both CTAs' samples
         for (int b = 0; b < 2; ++b) {
             for (int m = 0; m < MAX_MT; ++m) mbar_init(&bars->act_ready[b][m], W_EPI);
             for (int j = 0; j < 2; ++j) mbar_init(&bars->acc_full[b][j], 1);
@@ -717,17 +717,22 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
       }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        // ================================================================= epilogue: set h = the samples of CTA h
-        const int h = (warp - W_EPI0) >> 2, q4 = warp & 3;
+        // ================================================================= epilogue
+        // A CTA's accumulators are its 128 neurons x the 128 samples of BOTH CTAs; the 64 columns of the other CTA's samples go to
+        // that CTA's operand buffer over DSMEM (32 KB per pair-tile and direction, while the tensor pipe reads the same shared
+        // memory at ~80 B/cycle).  Every warp takes two 16-sample blocks of the REMOTE set first and two of the local set after
+        // them, so that all eight warps feed the link from the start.  Measured per pair-tile: first tcgen05.ld 0.65 k cycles,
+        // four blocks 1.7 k, proxy fence 0.1 k after local stores but 1.6 k after remote ones: the drain of the remote stores is what
+        // bounds a pair-tile's epilogue at ~4 k cycles (one set per warp: 4.1 k; this order: 2.6-4.5 k).
+        const int hh = (warp - W_EPI0) >> 2, q4 = warp & 3;          // hh: blocks 2 hh, 2 hh + 1 of either set
         const int row = q4 * 32 + lane;
-        const uint32_t taddr_row = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(TSW * h);
-        const uint32_t xdst = mapa_u32(smem_u32(sX), (uint32_t)h);
-        const bool local = h == (int)rank;
+        const uint32_t taddr_q = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const uint32_t xdst2[2] = {mapa_u32(smem_u32(sX), 0u), mapa_u32(smem_u32(sX), 1u)};
         uint32_t acc_bits = 0;
         int gl = 0;
         for (int it = 0; it < n_iter; ++it) {
             const int par = it & 1;
-            float zsum[4] = {0.f, 0.f, 0.f, 0.f};         // lane pair (2 s, 2 s + 1): sample 16 blk + s of CTA h, summed over this warp's neurons
+            float zsum[4] = {0.f, 0.f, 0.f, 0.f};         // unit u; lane pair (2 s, 2 s + 1): sample 16 (2 hh + (u & 1)) + s of its set, summed over this warp's neurons
             for (int l = 0; l < L; ++l, ++gl) {
                 const int buf = gl & 1, N = p.widths[l], npad = layer_n(l), MT = n_mtiles(npad), PT = (MT + 1) / 2;
                 const bool last = (l == L - 1);
@@ -752,11 +757,14 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     const int rows_valid = max(0, min(128, npad - t * 128));
                     const float bb = bb2[j], ff = ff2[j];
                     if (q4 * 32 < rows_valid) {
-                        const uint32_t xc = xdst + (uint32_t)((n >> 6) * CH + (n & 63) * 16);
+                        const uint32_t xoff = (uint32_t)((n >> 6) * CH + (n & 63) * 16);
 #pragma unroll
-                        for (int blk = 0; blk < 4; ++blk) {
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t set = u < 2 ? (rank ^ 1u) : rank;             // remote first
+                            const int blk = 2 * hh + (u & 1);
+                            const uint32_t xc = xdst2[set] + xoff;
                             uint32_t d[16];
-                            tmem_ld16(taddr_row + (uint32_t)(buf * 256 + j * 128 + 16 * blk), d);
+                            tmem_ld16(taddr_q + (uint32_t)(buf * 256 + j * 128) + (uint32_t)TSW * set + (uint32_t)(16 * blk), d);
                             tmem_ld_wait();
                             if (last) {
                                 float v[16];
@@ -773,7 +781,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                                         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                                     }
                                 }
-                                zsum[blk] += v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+                                zsum[u] += v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
                             } else if (row < rows_valid) {
 #pragma unroll
                                 for (int g = 0; g < 2; ++g) {
@@ -798,8 +806,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                         }
                     }
                     if (!last && t * 128 < npad) {
-                        if (local) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        else asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+                        asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_remote_cta(mapa_u32(smem_u32(&bars->act_ready[(gl + 1) & 1][t]), 0));
@@ -807,16 +814,18 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     if (threadIdx.x == 32 * W_EPI0 && it < 2 && l < 4) FZ_CLK(65 + 16 * it + 4 * l + 2 * j);
                 }
             }
-            // this warp's partial sums of CTA h's 64 samples -> CTA h
+            // this warp's partial sums of its blocks of either set -> the CTA that owns the samples
             if ((lane & 1) == 0) {
 #pragma unroll
-                for (int blk = 0; blk < 4; ++blk)
-                    st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][q4][16 * blk + (lane >> 1)]), (uint32_t)h), zsum[blk]);
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t set = u < 2 ? (rank ^ 1u) : rank;
+                    st_cluster_f32(mapa_u32(smem_u32(&bars->red[rank][q4][16 * (2 * hh + (u & 1)) + (lane >> 1)]), set), zsum[u]);
+                }
             }
             asm volatile("fence.acq_rel.cluster;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fin), (uint32_t)h));
+            if (lane < 2) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->fin), (uint32_t)lane));
             if (warp == W_EPI0) {
                 // this CTA's samples of the tile: shallow part + the partial sums of both CTAs' neuron tiles
                 mbar_wait_cluster(&bars->fin, (uint32_t)par, p.err, 34);
