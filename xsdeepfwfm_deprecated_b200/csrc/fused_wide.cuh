@@ -727,7 +727,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         const int hh = (warp - W_EPI0) >> 2, q4 = warp & 3;          // hh: blocks 2 hh, 2 hh + 1 of either set
         const int row = q4 * 32 + lane;
         const uint32_t taddr_q = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        const uint32_t xdst2[2] = {mapa_u32(smem_u32(sX), 0u), mapa_u32(smem_u32(sX), 1u)};
+        const uint32_t xdst_loc = mapa_u32(smem_u32(sX), rank), xdst_rem = mapa_u32(smem_u32(sX), rank ^ 1u);
         uint32_t acc_bits = 0;
         int gl = 0;
         for (int it = 0; it < n_iter; ++it) {
@@ -762,7 +762,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                         for (int u = 0; u < 4; ++u) {
                             const uint32_t set = u < 2 ? (rank ^ 1u) : rank;             // remote first
                             const int blk = 2 * hh + (u & 1);
-                            const uint32_t xc = xdst2[set] + xoff;
+                            const uint32_t xc = (u < 2 ? xdst_rem : xdst_loc) + xoff;
                             uint32_t d[16];
                             tmem_ld16(taddr_q + (uint32_t)(buf * 256 + j * 128) + (uint32_t)TSW * set + (uint32_t)(16 * blk), d);
                             tmem_ld_wait();
