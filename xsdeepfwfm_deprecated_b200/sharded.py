@@ -17,7 +17,7 @@ Three exchange modes produce bit-identical logits (rows are copied, never summed
     shards and puts the P pointers into the field descriptors.  The SAME fused kernel then loads a row from whichever GPU
     owns it -- over NVLink 5 / NVSwitch when it is a peer -- straight into the registers of its gather warps.  Gather,
     exchange, FwFM interaction and MLP are one kernel: no index exchange, no staging buffers, no collective on the data
-    path (1230 M samples/s on 8 GPUs).
+    path (1260 M samples/s on 8 GPUs).
 
 ``p2p_pull`` (an option; measured slower than ``p2p`` at 2 and 8 GPUs; needs ``use_fwlw=1``)
     The same peer loads, issued by a separate small kernel (``dfw_pull_rows``) one batch AHEAD of the fused kernel: its
