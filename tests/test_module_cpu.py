@@ -95,3 +95,27 @@ def test_index_dtype_switch_is_validated():
     assert build(c["cfg"], index_dtype="int32").index_dtype == "int32"
     with pytest.raises(ValueError):
         build(c["cfg"], index_dtype="int16")
+
+
+def test_eval_and_train_keep_the_plan():
+    """predict_proba / eval_by_batch call eval() on every call; that must not throw the packed images away.
+    Parameter edits are caught by stale() (data_ptr + _version), device moves and load_state_dict still drop the plan."""
+    c = load_case(CASES[0])
+    m = build(c["cfg"]).eval()
+    sentinel = object()
+    m._plan = sentinel
+    m.eval(); m.eval()
+    assert m._plan is sentinel
+    m.train()                                    # a mode CHANGE drops it: fit() prunes with .data[mask] = 0 in train mode
+    assert m._plan is None
+    m._plan = sentinel
+    m.train(); m.train()
+    assert m._plan is sentinel
+    m.eval()
+    assert m._plan is None
+    m._plan = sentinel
+    m.load_state_dict(m.state_dict())
+    assert m._plan is None
+    m._plan = sentinel
+    m.float()                                    # _apply: tensors may be re-bound
+    assert m._plan is None

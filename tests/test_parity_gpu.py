@@ -146,7 +146,11 @@ def test_in_place_pruning_is_seen_after_eval():
     c = load_case("deepfwfm_fwlw")
     m = to_cuda(c["cfg"], c["weights"])
     before = run(m, c["Xi"], c["Xv"])
+    plan = m._plan
+    m.eval()                                     # already in eval mode: the packed images survive
+    assert m._plan is plan
     pruned = prune.one_shot_prune(c["weights"], 0.9, 0.444, 1.0)
+    m.train()                                    # fit() runs in train mode
     with torch.no_grad():
         for k, p in m.named_parameters():
             p.data[torch.from_numpy(pruned[k] == 0).cuda() & (p.data != 0)] = 0
@@ -155,6 +159,15 @@ def test_in_place_pruning_is_seen_after_eval():
     ref = closed_form.forward(c["cfg"], pruned, c["Xi"], c["Xv"])["logit"]
     assert np.abs(after - ref).max() <= logit_tol(ref, FP32_REL)
     assert np.abs(after - before).max() > 1e-3
+    # the same edit without leaving eval mode is picked up by repack()
+    m2 = to_cuda(c["cfg"], c["weights"])
+    run(m2, c["Xi"], c["Xv"])
+    with torch.no_grad():
+        for k, p in m2.named_parameters():
+            p.data[torch.from_numpy(pruned[k] == 0).cuda() & (p.data != 0)] = 0
+    m2.repack()
+    again = run(m2, c["Xi"], c["Xv"])
+    assert np.array_equal(again, after)
 
 
 def test_table_and_mlp_edits_are_live_without_any_repack():

@@ -166,7 +166,8 @@ class _Plan:
     def stale(self) -> bool:
         """Re-bound storage (init_weights, .cuda()) or an in-place edit that autograd's version counter sees (copy_, mul_, an
         optimizer step).  Edits through ``param.data[...] = ...`` (the reference's pruner) bypass that counter: tables and fp32
-        MLP weights are read in place anyway, the derived images (shallow image, bf16 / CSR weights) need eval() / repack()."""
+        MLP weights are read in place anyway, the derived images (shallow image, bf16 / CSR weights) need a train() -> eval()
+        transition (what the reference's fit() / eval_by_batch() flow does) or repack()."""
         return self.ptrs != tuple((p.data_ptr(), p._version) for p in self.params)
 
     # -- derived images ------------------------------------------------------------------
@@ -438,7 +439,12 @@ class DeepFMs(nn.Module):
         return super()._apply(fn, *a, **kw)
 
     def train(self, mode: bool = True):
-        self._plan = None
+        # The plan (pointer table, packed weight images, workspace) is dropped only when the mode CHANGES: the reference's flow is
+        # fit() [train mode: param.data[mask] = 0 pruning, invisible to the version counters] -> eval() -> inference, and that
+        # transition must rebuild the images.  predict_proba / eval_by_batch call eval() on every call; rebuilding the plan there
+        # cost milliseconds around a ~30 us kernel.  `.data[...]` edits made while staying in eval mode need repack().
+        if bool(mode) != self.training:
+            self._plan = None
         return super().train(mode)
 
     def load_state_dict(self, *a, **kw):
