@@ -12,8 +12,8 @@
 //     thread owns (sample, embedding column), loads its column of every field's row straight into registers (ten lanes cover
 //     one 40-byte row, three rows per warp instruction -- whole sectors, no cp.async pieces, no fix-up pass), holds the first
 //     32 samples' values while the previous tile's last layer still reads X, and writes the bf16 (hi | lo) operand the moment
-//     the tensor pipe releases X (x_free = tcgen05.commit after the tile's last MMA).  First order + FwFM second order then run
-//     from the registers under layer 1's MMAs, as before.
+//     the tensor pipe releases X (x_free = tcgen05.commit after the tile's last MMA).  First order + FwFM second order run
+//     from the registers: one sample's while waiting for that release, the other's under layer 1's MMAs.
 //   * one MMA issuer, one weight ring, and a HYBRID order inside a layer: [pair-tile 0: chunks 0-3][pair-tile 1: chunks 0-3]
 //     [pair-tile 0: chunks 4..][pair-tile 1: chunks 4..].  Pair-tile 0 (neurons 0..255 = the next layer's chunks 0-3) completes a
 //     quarter of a layer early, its epilogue runs under pair-tile 1's last MMAs, and the next layer starts on chunks 0-3 while
@@ -22,14 +22,16 @@
 //   * the dense field matrix is always the kernel-parameter (constant-bank) form; a pruned R runs through it with its zeros
 //     (the pair-list walk needed the fp32 block).
 //
-//   warps 0      TMA producer (both CTAs): its own 128-row half of every (pair-tile, chunk[, hi|lo]) box, ring of NS slots,
-//                signals the LEADER's full[slot] (cp.async.bulk.tensor ... cta_group::2), which expects both halves
-//   warp  1      MMA issuer (leader only): tcgen05.mma.cta_group::2, commits multicast to both CTAs
-//   warps 2-3    idle (keep warp % 4 == TMEM lane quarter for the epilogue warps)
-//   warps 4-11   epilogue: set h = (warp - 4) / 4 takes sample columns [64 h, 64 h + 64) of each pair-tile = the samples of CTA h;
-//                thread = neuron (TMEM lane).  + bias, ReLU, split to bf16 hi/lo, 16-byte stores into CTA h's X
-//                (st.shared::cluster to the peer); last layer: x net_1_fc, warp transpose-reduction into CTA h's `red`
-//   warps 12-23  gather group: 3 samples x 10 columns per warp, two rounds of 32 samples per tile
+// Roles by warp id (a warp's scheduler is warp % 4; a warpgroup -- the setmaxnreg granule -- is four consecutive warps):
+//   warp  3          MMA issuer (leader only): tcgen05.mma.cta_group::2, commits multicast to both CTAs.  Scheduler 3 holds
+//                    nothing else that is busy: two epilogue warps and the three producers, all mostly asleep.
+//   warps 15, 19, 23 TMA producers (both CTAs), boxes round-robin: this CTA's 128-row half of every (pair-tile, chunk[, hi|lo])
+//                    box into a ring of NS slots; signals the LEADER's full[slot] (cp.async.bulk.tensor ... cta_group::2)
+//   warps 4-11       epilogue; thread = neuron (TMEM lane quarter = warp % 4).  Warp (hh, q4) takes 16-sample blocks 2 hh, 2 hh + 1 of
+//                    the REMOTE CTA's 64 sample columns first (st.shared::cluster into the peer's X), then of its own: + bias,
+//                    ReLU, split to bf16 hi/lo, 16-byte stores; last layer: x net_1_fc, warp transpose-reduction into the
+//                    owning CTA's `red`.  Warp 4 also finishes the tile (shallow + deep sums, sigmoid, store).
+//   warps 0-2, 12-14, 16-18, 20-22   gather group (12 warps): 3 x 2 samples x 10 columns per warp
 #pragma once
 #include "fused_pair.cuh"
 
@@ -38,7 +40,7 @@ namespace fz {
 namespace wd {
 
 constexpr int TSW = 64;                        // samples per CTA and tile
-constexpr int W_MMA = 3, N_PROD = 3;          // producers: warps 0, 1, 2
+constexpr int W_MMA = 3, N_PROD = 3;          // producers: warp 3 of warpgroups 3, 4, 5 (15, 19, 23)
 constexpr int W_EPI0 = 4, W_EPI = 8;
 constexpr int W_G0 = W_EPI0 + W_EPI, W_G = 12;
 constexpr int THREADS = 32 * (W_G0 + W_G);     // 768: 80 registers per thread
@@ -60,7 +62,7 @@ struct WideBars {
                                      // concurrent multi-tile launches that store to host memory)
     uint64_t act_ready[2][MAX_MT];   // leader: [layer parity][neuron tile], W_EPI arrives from the CTA that owns the tile
     uint64_t acc_full[2][2];         // per CTA: [layer parity][pair-tile] accumulators complete (multicast commit)
-    uint64_t fin;                    // per CTA: the partial sums of its samples are in `red` (2 x 4 arrives per tile)
+    uint64_t fin;                    // per CTA: the partial sums of its samples are in `red` (2 x W_EPI arrives per tile)
     uint32_t tmem_holder, pad_;
     float shallow[2][TSW];           // [tile parity]
     float red[2][4][TSW];            // [source CTA][lane quarter][sample] (one buffer: a warp writes tile t + 1 only after every
