@@ -54,6 +54,8 @@ struct WideBars {
     uint64_t full[NS_MAX];           // leader: both CTAs' boxes of the slot have landed
     uint64_t empty[NS_MAX];          // per CTA: slot consumed (multicast commit)
     uint64_t x_ready;                // leader: layer-1 operand of the tile written in both CTAs (2 x W_G arrives)
+    uint64_t x_ready03;              // leader: chunks 0-3 of it (k < 256) are written: layer 1 starts on them while the gather still
+                                     // waits for the previous tile's last MMAs to release chunks 4..
     uint64_t x_free;                 // per CTA: every MMA of the tile has completed, X may be overwritten (multicast commit)
     uint64_t x_free03;               // per CTA: chunks 0-3 of X are dead already (after segment 2 of the tile's last layer)
     uint64_t shallow_ready[2];       // per CTA, [tile parity]: W_G arrives per tile.  Two barriers because its waiter (the finisher) is not
@@ -386,6 +388,7 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS_MAX; ++s) { mbar_init(&bars->full[s], (uint32_t)wp.grp); mbar_init(&bars->empty[s], 1); }
         mbar_init(&bars->x_ready, 2 * W_G);
+        mbar_init(&bars->x_ready03, 2 * W_G);
         mbar_init(&bars->x_free, 1);
         mbar_init(&bars->x_free03, 1);
         mbar_init(&bars->shallow_ready[0], W_G);
@@ -457,6 +460,8 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
         const int sa = 2 * slot;                                // tile-local samples sa, sa + 1
         const bool fwlw = ep.flags & DFW_USE_FWLW;
         constexpr int FSPLIT = 256 / KT;                        // fields [0, FSPLIT) lie entirely in chunks 0-3 of X (k < 256)
+        constexpr int KB = 256 - FSPLIT * KT;                   // columns of field FSPLIT that still do
+        static_assert(FSPLIT < FT, "layer 1 has more than four K chunks for the dataset shapes");
         bool joined = false;
         int gmode = GM_PLAIN, qop = DFW_TABLE_PLAIN;           // qop: THE operation of a QR model (GM_QR needs a single one)
         for (int it = 0; it < n_iter; ++it) {
@@ -522,10 +527,22 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                     // rest after its last MMA
                     if (it > 0) mbar_wait(&bars->x_free03, (uint32_t)((it - 1) & 1), p.err, 40);
                     if (gtid == 0 && it < 4) FZ_CLK(100 + 8 * it);
-                    if (owner) wide_write2<SPLIT, FT, KT, 0, FSPLIT>(sX, sa, kk, e0, e1);
+                    // columns k < 256 (chunks 0-3): fields [0, FSPLIT) and the first KB columns of field FSPLIT, which straddles
+                    // the boundary.  Layer 1's first two segments read nothing else, so they get their own barrier: the issuer goes
+                    // from the previous tile's last MMA straight into them, and the rest of X is written underneath.
+                    if (owner) {
+                        wide_write2<SPLIT, FT, KT, 0, FSPLIT>(sX, sa, kk, e0, e1);
+                        if constexpr (KB > 0) { if (kk < KB) wide_write2<SPLIT, FT, KT, FSPLIT, FSPLIT + 1>(sX, sa, kk, e0, e1); }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote_cta(mapa_u32(smem_u32(&bars->x_ready03), 0));
                     if (it > 0) mbar_wait(&bars->x_free, (uint32_t)((it - 1) & 1), p.err, 41);
                     if (gtid == 0 && it < 4) FZ_CLK(97 + 8 * it);
-                    if (owner) wide_write2<SPLIT, FT, KT, FSPLIT, FT>(sX, sa, kk, e0, e1);
+                    if (owner) {
+                        if constexpr (KB > 0) { if (kk >= KB) wide_write2<SPLIT, FT, KT, FSPLIT, FSPLIT + 1>(sX, sa, kk, e0, e1); }
+                        wide_write2<SPLIT, FT, KT, FSPLIT + (KB > 0 ? 1 : 0), FT>(sX, sa, kk, e0, e1);
+                    }
                     // K padding columns [F*K, Kp) of all 64 samples are zero
                     for (int i = gtid; i < TSW * (Kp - FK); i += G_THREADS_W) {
                         const int sp = i / (Kp - FK), col = FK + (i - sp * (Kp - FK));
@@ -657,8 +674,11 @@ fused_wide_kernel(const __grid_constant__ Maps maps, const __grid_constant__ UPa
                                 if (l == 0) {
                                     if (c == 0) {
                                         if (lane == 0 && it < 4) FZ_CLK(32 + 8 * it);
-                                        mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 21);
+                                        mbar_wait_cluster(&bars->x_ready03, (uint32_t)(it & 1), p.err, 21);
+                                        if (kch <= sp) mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 23);
                                         if (lane == 0 && it < 4) FZ_CLK(33 + 8 * it);
+                                    } else if (c == sp) {
+                                        mbar_wait_cluster(&bars->x_ready, (uint32_t)(it & 1), p.err, 23);     // chunks 4..
                                     }
                                 } else if ((c & 1) == 0) {
                                     const int g = c >> 1, bit = buf * MAX_MT + g;
