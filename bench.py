@@ -597,6 +597,26 @@ def run_ours(args):
             e2e["int32_indices"] = {"error": str(ex)[:200]}
     clk = clocks.stop() if rank == 0 else None
 
+    # supplementary: the public module in a plain Python loop (one ctypes call per step on one stream: no graph, no launches in flight)
+    eager = None
+    if rank == 0 and world == 1:
+        try:
+            with torch.no_grad():
+                for j in range(3):
+                    model(Xi[j % nb], Xv[j % nb])
+                torch.cuda.synchronize(device)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                for j in range(args.steps):
+                    model(Xi[j % nb], Xv[j % nb])
+                eb.record()
+                eb.synchronize()
+            ems = ea.elapsed_time(eb) / args.steps
+            eager = dict(value=round(B / (ems * 1e-3), 1), unit=UNIT, ms_per_step=round(ems, 4),
+                         what="model(Xi, Xv) in a Python loop, device-resident inputs, one stream, no CUDA graph")
+        except Exception as ex:        # supplementary only: never lose the bench line over it
+            eager = {"error": str(ex)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_baseline(B, args.cpu_seconds)
@@ -622,7 +642,7 @@ def run_ours(args):
                                     if not pull else "rows fetched by direct peer loads over NVLink (no collective) by a pull kernel "
                                     "that runs ahead of the fused kernel into a local staging buffer (exchange='p2p_pull')")},
             "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "clocks": clk,
-            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda,
+            "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": ref_cuda, "eager_loop": eager,
         }
         print(json.dumps(out))
     if dist:
